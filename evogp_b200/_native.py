@@ -1,0 +1,86 @@
+"""Loads the two native libraries and exposes the C ABI through ctypes.
+
+Fails loudly (RuntimeError) when a library is missing — the product has no CPU or
+pure-PyTorch fallback for any operator.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libevogp_b200.so")
+OPS_PATH = os.path.join(_PKG, "lib", "evogp_cuda_ops.so")
+
+_abi = None
+_ops_loaded = False
+
+# every symbol include/evogp_b200.h declares
+ABI_SYMBOLS = (
+    "evogp_version", "evogp_last_error", "evogp_launch_count", "evogp_generate", "evogp_mutate", "evogp_crossover",
+    "evogp_eval_workspace_bytes", "evogp_evaluate", "evogp_SR_fitness", "evogp_batch_forward",
+    "evogp_SR_fitness_host", "evogp_host_release",
+)
+
+
+def _missing(path):
+    return RuntimeError(
+        f"{path} not found: build the native libraries first (python -m evogp_b200.build). "
+        "evogp_b200 has no CPU / PyTorch fallback."
+    )
+
+
+def abi():
+    """ctypes handle of libevogp_b200.so with argtypes set."""
+    global _abi
+    if _abi is not None:
+        return _abi
+    if not os.path.exists(LIB_PATH):
+        raise _missing(LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, u, i, f, sz = C.c_void_p, C.c_uint, C.c_int, C.c_float, C.c_size_t
+    L.evogp_version.restype = i
+    L.evogp_last_error.restype = C.c_char_p
+    L.evogp_launch_count.restype = C.c_ulonglong
+    L.evogp_eval_workspace_bytes.restype = sz
+    L.evogp_eval_workspace_bytes.argtypes = [u, u]
+    L.evogp_generate.argtypes = [u, u, u, u, u, f, f, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.evogp_mutate.argtypes = [i, i] + [vp] * 11
+    L.evogp_crossover.argtypes = [i, i, i] + [vp] * 11
+    L.evogp_evaluate.argtypes = [u, u, u, u, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.evogp_SR_fitness.argtypes = [u, u, u, u, u, i, vp, vp, vp, vp, vp, vp, u, vp, sz, vp]
+    L.evogp_batch_forward.argtypes = [u, u, u, u, u, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.evogp_SR_fitness_host.argtypes = [u, u, u, u, u, i, vp, vp, vp, vp, vp, vp, i]
+    L.evogp_host_release.restype = None
+    for name in ("evogp_generate", "evogp_mutate", "evogp_crossover", "evogp_evaluate", "evogp_SR_fitness",
+                 "evogp_batch_forward", "evogp_SR_fitness_host"):
+        getattr(L, name).restype = i
+    _abi = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {abi().evogp_last_error().decode()}")
+
+
+def load_ops():
+    """Registers torch.ops.evogp_cuda.* (idempotent)."""
+    global _ops_loaded
+    if _ops_loaded:
+        return
+    if not os.path.exists(OPS_PATH):
+        raise _missing(OPS_PATH)
+    abi()
+    torch.ops.load_library(OPS_PATH)
+    _ops_loaded = True
+
+
+def launch_count():
+    return int(abi().evogp_launch_count())
+
+
+def device():
+    """The device Forest tensors live on: the current CUDA device of this process
+    (one process per GPU; torch.cuda.set_device(local_rank) selects it)."""
+    return torch.device("cuda", torch.cuda.current_device())

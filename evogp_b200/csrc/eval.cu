@@ -1,0 +1,520 @@
+// eval.cu — batched expression-tree evaluation on sm_100a.
+//
+// Replaces the reference's evaluate / SR_fitness host functions
+// (src/evogp/cuda/forward.cu:353-371, :827-856) and the four kernels behind them
+// (:304-351, :402-479, :591-647, :738-779), and fuses Forest.batch_forward
+// (tree/forest.py:143-176).
+//
+// Two kernels:
+//   lower_kernel  (lower.cuh)  packed rows -> accumulator-machine programs, 8 B/slot
+//   replay_kernel (here)       persistent CTAs; each WARP owns one tree at a time,
+//        lanes own datapoints (K per lane, float4-vectorised), so the opcode
+//        dispatch is warp-uniform.  The next tree's program row is pulled into
+//        shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) while the
+//        current one replays; trees are handed out by an atomic ticket so ragged
+//        tree lengths balance.  The dataset is staged once per CTA, transposed to
+//        [var][datapoint].  Squared/absolute error is accumulated in registers and
+//        reduced with warp shuffles: one plain store per tree — no memset, no
+//        atomics on fitness, no averaging kernel.
+#include <cooperative_groups.h>
+#include "lower.cuh"
+
+namespace evogp {
+
+enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_OUTPUT = 2, MODE_ROWWISE = 3 };
+
+struct ReplayArgs {
+    const uint2 *prog;      // [P][Lp]
+    unsigned *sched;        // [0] ticket counter
+    const float *X;         // MODE_ROWWISE: [P][V]; else [N][V]
+    const float *labels;    // [N][O] (loss modes)
+    float *out;             // fitness[P] | results[P][N][O] | results[P][O]
+    int P, Lp, N, V, O;
+    int NP;                 // N rounded up to a whole number of passes
+    int npass, depth, mode;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#define FOR_K _Pragma("unroll") for (int k = 0; k < K; ++k)
+
+// A lane's K values of one vector live at  base + lane*VW + j*32*VW + r  (VW = min(K,4)):
+// float4 accesses for K >= 4, conflict-free for every K.
+template <int K>
+__device__ __forceinline__ void ld_vec(float (&r)[K], const float *p) {
+    if constexpr (K >= 4) {
+#pragma unroll
+        for (int j = 0; j < K / 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + j * 128);
+            r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+        }
+    } else {
+        FOR_K r[k] = p[k * 32];
+    }
+}
+template <int K>
+__device__ __forceinline__ void st_vec(float *p, const float (&r)[K]) {
+    if constexpr (K >= 4) {
+#pragma unroll
+        for (int j = 0; j < K / 4; ++j)
+            *reinterpret_cast<float4 *>(p + j * 128) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    } else {
+        FOR_K p[k * 32] = r[k];
+    }
+}
+// datapoint index (within a pass) of a lane's k-th value
+template <int K>
+__device__ __forceinline__ int dp_index(int lane, int k) {
+    if constexpr (K >= 4) return (k >> 2) * 128 + lane * 4 + (k & 3);
+    else return k * 32 + lane;
+}
+
+template <int K, bool MULTI, bool ROWWISE>
+__global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int VW = K >= 4 ? 4 : 1;
+    constexpr int SLOT = K * 32;                 // floats per stack slot / per output accumulator
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane_off = lane * VW;
+
+    // ---- shared memory carve-up ----
+    float *Xs = reinterpret_cast<float *>(smem_raw);                    // [V][NP]   (not ROWWISE)
+    float *Ys = Xs + (ROWWISE ? 0 : (size_t)g.V * g.NP);                // [O][NP]   (loss modes)
+    float *after = Ys + ((g.mode <= MODE_ABS) ? (size_t)g.O * g.NP : 0);
+    uint2 *progs = reinterpret_cast<uint2 *>(after) + (size_t)warp * 2 * g.Lp;          // 2 rows / warp
+    float *stacks = reinterpret_cast<float *>(reinterpret_cast<uint2 *>(after) + (size_t)nwarp * 2 * g.Lp);
+    float *stack = stacks + (size_t)warp * g.depth * SLOT;
+    float *outs_all = stacks + (size_t)nwarp * g.depth * SLOT;          // [O][SLOT] / warp (MULTI)
+    float *outs = outs_all + (MULTI ? (size_t)warp * g.O * SLOT : 0);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(outs_all + (MULTI ? (size_t)nwarp * g.O * SLOT : 0)) + warp * 2;
+
+    // ---- stage the dataset once per CTA: X[N][V] -> Xs[V][NP], labels[N][O] -> Ys[O][NP] ----
+    if constexpr (!ROWWISE) {
+        const int tot = g.NP * g.V;
+        for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+            const int d = idx / g.V, v = idx - d * g.V;
+            Xs[v * g.NP + d] = d < g.N ? __ldg(g.X + idx) : 0.0f;
+        }
+        if (g.mode <= MODE_ABS) {
+            const int tl = g.NP * g.O;
+            for (int idx = threadIdx.x; idx < tl; idx += blockDim.x) {
+                const int d = idx / g.O, o = idx - d * g.O;
+                Ys[o * g.NP + d] = d < g.N ? __ldg(g.labels + idx) : 0.0f;
+            }
+        }
+    }
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t row_bytes = (uint32_t)g.Lp * 8u;
+    uint32_t phase0 = 0, phase1 = 0;
+    int buf = 0;
+    int tree = 0;
+    if (lane == 0) tree = (int)atomicAdd(g.sched, 1u);
+    tree = __shfl_sync(0xffffffffu, tree, 0);
+    if (lane == 0 && tree < g.P) {
+        mbar_expect_tx(bars, row_bytes);
+        tma_load_1d(progs, g.prog + (size_t)tree * g.Lp, row_bytes, bars);
+    }
+
+    while (tree < g.P) {
+        // ticket + prefetch for the tree after this one
+        int next = 0;
+        if (lane == 0) {
+            next = (int)atomicAdd(g.sched, 1u);
+            if (next < g.P) {
+                mbar_expect_tx(bars + (buf ^ 1), row_bytes);
+                tma_load_1d(progs + (size_t)(buf ^ 1) * g.Lp, g.prog + (size_t)next * g.Lp, row_bytes, bars + (buf ^ 1));
+            }
+        }
+        next = __shfl_sync(0xffffffffu, next, 0);
+        if (buf == 0) { mbar_wait(bars, phase0); phase0 ^= 1; }
+        else          { mbar_wait(bars + 1, phase1); phase1 ^= 1; }
+        const uint2 *prog = progs + (size_t)buf * g.Lp;
+
+        float err = 0.0f;
+        for (int pass = 0; pass < g.npass; ++pass) {
+            const int pass_off = pass * SLOT;
+            const float *xl;
+            if constexpr (ROWWISE) xl = g.X + (size_t)tree * g.V;
+            else xl = Xs + pass_off + lane_off;
+
+            auto fetch = [&](float(&l)[K], bool is_const, float cst, uint32_t idx) {
+                if (is_const) {
+                    FOR_K l[k] = cst;
+                } else if constexpr (ROWWISE) {
+                    const float x = __ldg(xl + idx);
+                    FOR_K l[k] = x;
+                } else {
+                    ld_vec<K>(l, xl + (size_t)idx * g.NP);
+                }
+            };
+
+            float acc[K];
+            FOR_K acc[k] = 0.0f;
+            if constexpr (MULTI) {
+                for (int o = 0; o < g.O; ++o) {
+                    float z[K];
+                    FOR_K z[k] = 0.0f;
+                    st_vec<K>(outs + o * SLOT + lane_off, z);
+                }
+            }
+            int sp = 0, pc = 0;
+            uint2 ins = prog[0];
+            while (true) {
+                const uint32_t w = ins.x;
+                const float cst = __uint_as_float(ins.y);
+                ++pc;
+                ins = prog[pc < g.Lp ? pc : g.Lp - 1];   // prefetch the next slot
+                if (w & I_PUSH) {
+                    st_vec<K>(stack + sp * SLOT + lane_off, acc);
+                    ++sp;
+                }
+                const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
+
+// result r, forwarded value `right` (only used by multi-output nodes)
+#define FINISH(r, right)                                                          \
+    if constexpr (MULTI) {                                                        \
+        if (w & I_OUT) {                                                          \
+            if (ib != I_IDX_MASK) {                                               \
+                float o_[K];                                                      \
+                ld_vec<K>(o_, outs + ib * SLOT + lane_off);                       \
+                FOR_K o_[k] += r[k];                                              \
+                st_vec<K>(outs + ib * SLOT + lane_off, o_);                       \
+            }                                                                     \
+            FOR_K acc[k] = right[k];                                              \
+        } else {                                                                  \
+            FOR_K acc[k] = r[k];                                                  \
+        }                                                                         \
+    } else {                                                                      \
+        FOR_K acc[k] = r[k];                                                      \
+    }
+
+#define CASE_U(u)                                                                 \
+    case C_UA + u: {                                                              \
+        float r[K];                                                               \
+        FOR_K r[k] = unary_op<u>(acc[k]);                                         \
+        FINISH(r, acc)                                                            \
+    } break;                                                                      \
+    case C_UL + u: {                                                              \
+        float l[K], r[K];                                                         \
+        fetch(l, w & I_ACONST, cst, ia);                                          \
+        FOR_K r[k] = unary_op<u>(l[k]);                                           \
+        FINISH(r, l)                                                              \
+    } break;
+
+#define CASE_B(b)                                                                 \
+    case C_AL + b: {                                                              \
+        float l[K], r[K];                                                         \
+        fetch(l, w & I_ACONST, cst, ia);                                          \
+        FOR_K r[k] = binary_op<b>(acc[k], l[k]);                                  \
+        FINISH(r, l)                                                              \
+    } break;                                                                      \
+    case C_LA + b: {                                                              \
+        float l[K], r[K];                                                         \
+        fetch(l, w & I_ACONST, cst, ia);                                          \
+        FOR_K r[k] = binary_op<b>(l[k], acc[k]);                                  \
+        FINISH(r, acc)                                                            \
+    } break;                                                                      \
+    case C_LL + b: {                                                              \
+        float l[K], m[K];                                                         \
+        fetch(l, w & I_ACONST, cst, ia);                                          \
+        fetch(m, w & I_BCONST, cst, ib);                                          \
+        FOR_K acc[k] = binary_op<b>(l[k], m[k]);                                  \
+    } break;                                                                      \
+    case C_SA + b: {                                                              \
+        float s[K], r[K];                                                         \
+        --sp;                                                                     \
+        ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
+        FOR_K r[k] = binary_op<b>(s[k], acc[k]);                                  \
+        FINISH(r, acc)                                                            \
+    } break;                                                                      \
+    case C_AS + b: {                                                              \
+        float s[K], r[K];                                                         \
+        --sp;                                                                     \
+        ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
+        FOR_K r[k] = binary_op<b>(acc[k], s[k]);                                  \
+        FINISH(r, s)                                                              \
+    } break;
+
+                switch (w & 0xFFu) {
+                case C_END: goto tree_done;
+                case C_LOAD: fetch(acc, w & I_ACONST, cst, ia); break;
+                case C_NAN: { FOR_K acc[k] = __int_as_float(0x7fc00000); } break;
+                case C_IF: {
+                    float t1[K], t2[K], a[K], b[K], c[K], r[K];
+                    sp -= 2;
+                    ld_vec<K>(t1, stack + (sp + 1) * SLOT + lane_off);
+                    ld_vec<K>(t2, stack + sp * SLOT + lane_off);
+                    const uint32_t sa = ia & 3, sb = (ia >> 2) & 3, sc = (ia >> 4) & 3;
+                    FOR_K {
+                        a[k] = sa == 0 ? acc[k] : (sa == 1 ? t1[k] : t2[k]);
+                        b[k] = sb == 0 ? acc[k] : (sb == 1 ? t1[k] : t2[k]);
+                        c[k] = sc == 0 ? acc[k] : (sc == 1 ? t1[k] : t2[k]);
+                        r[k] = a[k] > 0.0f ? b[k] : c[k];   // forward.cu:223
+                    }
+                    FINISH(r, c)
+                } break;
+                    CASE_U(0) CASE_U(1) CASE_U(2) CASE_U(3) CASE_U(4) CASE_U(5) CASE_U(6) CASE_U(7)
+                    CASE_U(8) CASE_U(9) CASE_U(10) CASE_U(11) CASE_U(12) CASE_U(13) CASE_U(14) CASE_U(15)
+                    CASE_B(0) CASE_B(1) CASE_B(2) CASE_B(3) CASE_B(4) CASE_B(5) CASE_B(6)
+                    CASE_B(7) CASE_B(8) CASE_B(9) CASE_B(10) CASE_B(11) CASE_B(12) CASE_B(13)
+                default: break;
+                }
+                if (pc >= g.Lp) break;
+            }
+        tree_done:
+            // ---- per-pass epilogue ----
+            if (g.mode <= MODE_ABS) {
+                if constexpr (MULTI) {
+                    for (int o = 0; o < g.O; ++o) {
+                        float y[K], r[K];
+                        ld_vec<K>(y, Ys + (size_t)o * g.NP + pass_off + lane_off);
+                        ld_vec<K>(r, outs + o * SLOT + lane_off);
+                        FOR_K {
+                            const float diff = y[k] - r[k];
+                            const float e = g.mode == MODE_MSE ? diff * diff : fabsf(diff);
+                            if (pass_off + dp_index<K>(lane, k) < g.N) err += e;
+                        }
+                    }
+                } else {
+                    float y[K];
+                    ld_vec<K>(y, Ys + pass_off + lane_off);
+                    FOR_K {
+                        const float diff = y[k] - acc[k];
+                        const float e = g.mode == MODE_MSE ? diff * diff : fabsf(diff);
+                        if (pass_off + dp_index<K>(lane, k) < g.N) err += e;
+                    }
+                }
+            } else if (g.mode == MODE_OUTPUT) {
+                FOR_K {
+                    const int d = pass_off + dp_index<K>(lane, k);
+                    if (d < g.N) {
+                        float *dst = g.out + ((size_t)tree * g.N + d) * g.O;
+                        if constexpr (MULTI) {
+                            for (int o = 0; o < g.O; ++o) dst[o] = outs[o * SLOT + lane_off + (K >= 4 ? (k >> 2) * 128 + (k & 3) : k * 32)];
+                        } else {
+                            dst[0] = acc[k];
+                        }
+                    }
+                }
+            } else {   // MODE_ROWWISE: every lane computed the same value; lane 0 stores
+                if (lane == 0) {
+                    float *dst = g.out + (size_t)tree * g.O;
+                    if constexpr (MULTI) {
+                        for (int o = 0; o < g.O; ++o) dst[o] = outs[o * SLOT];
+                    } else {
+                        dst[0] = acc[0];
+                    }
+                }
+            }
+        }
+        if (g.mode <= MODE_ABS) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) err += __shfl_xor_sync(0xffffffffu, err, s);
+            if (lane == 0) g.out[tree] = err / (float)(unsigned)g.N;   // forward.cu:478
+        }
+        __syncwarp();   // every lane is done with prog[buf] before lane 0 re-targets it
+        buf ^= 1;
+        tree = next;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int g_sm_count = 0, g_max_smem = 0;
+
+static int device_props() {
+    if (g_sm_count) return EVOGP_OK;
+    int dev = 0;
+    EVOGP_CUDA(cudaGetDevice(&dev));
+    EVOGP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    EVOGP_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return EVOGP_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int prog_pitch(unsigned L) { return (int)((L + 1) & ~1u); }
+
+struct Workspace {
+    uint2 *prog;
+    unsigned *sched;   // 4 words
+    unsigned *flags;   // 4 words
+};
+static size_t prog_bytes(unsigned P, unsigned L) { return (size_t)P * prog_pitch(L) * sizeof(uint2); }
+static Workspace carve(void *ws, unsigned P, unsigned L) {
+    Workspace w;
+    unsigned char *b = static_cast<unsigned char *>(ws);
+    w.sched = reinterpret_cast<unsigned *>(b);
+    w.flags = w.sched + 4;
+    w.prog = reinterpret_cast<uint2 *>(b + 256);
+    return w;
+}
+
+template <bool MULTI>
+static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
+                        const int16_t *type, const int16_t *size, int depth, cudaStream_t st) {
+    // threads per CTA limited by the [2][L][T] u32 scratch
+    int T = 128;
+    while (T > 32 && (size_t)2 * L * T * 4 > 160 * 1024) T -= 32;
+    const size_t smem = (size_t)2 * L * T * 4;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[MULTI]) {
+        EVOGP_CUDA(cudaFuncSetAttribute(lower_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[MULTI] = true;
+    }
+    LowerArgs a;
+    a.value = value; a.type = type; a.size = size;
+    a.prog = w.prog; a.sched = w.sched; a.flags = w.flags;
+    a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
+    lower_kernel<MULTI><<<(P + T - 1) / T, T, smem, st>>>(a);
+    count_launch();
+    return check_launch("lower_kernel");
+}
+
+// cost model for choosing K: issue slots per datapoint ~ (dispatch overhead + K) / K, times padding waste
+static int choose_k(int N) {
+    const int ks[3] = {8, 4, 1};
+    int best = 1;
+    double best_cost = 1e30;
+    for (int i = 0; i < 3; ++i) {
+        const int K = ks[i];
+        const int npass = (N + 32 * K - 1) / (32 * K);
+        const double cost = (double)npass * (14.0 + 2.0 * K);
+        if (cost < best_cost) { best_cost = cost; best = K; }
+    }
+    return best;
+}
+
+template <int K, bool MULTI, bool ROWWISE>
+static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
+    auto kern = replay_kernel<K, MULTI, ROWWISE>;
+    const int SLOT = K * 32;
+    a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
+    a.NP = a.npass * SLOT;
+    a.depth = depth;
+    const size_t data = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * a.NP * 4;
+    auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
+    int warps = 8;
+    while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
+    const size_t smem = data + warps * per_warp();
+    if (smem > (size_t)g_max_smem) {
+        set_error("dataset of %d x %d floats (+ labels) does not fit the %d B shared-memory staging area", a.N, a.V, g_max_smem);
+        return EVOGP_ERR_UNSUPPORTED;
+    }
+    EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long want = ((long long)a.P + warps - 1) / warps;
+    int grid = (int)(want < (long long)per_sm * g_sm_count ? want : (long long)per_sm * g_sm_count);
+    if (grid < 1) grid = 1;
+    kern<<<grid, warps * 32, smem, st>>>(a);
+    count_launch();
+    return check_launch("replay_kernel");
+}
+
+template <bool MULTI>
+static int launch_replay(const ReplayArgs &a, int depth, cudaStream_t st) {
+    if (a.mode == MODE_ROWWISE) return launch_replay_t<1, MULTI, true>(a, depth, st);
+    switch (choose_k(a.N)) {
+    case 8: return launch_replay_t<8, MULTI, false>(a, depth, st);
+    case 4: return launch_replay_t<4, MULTI, false>(a, depth, st);
+    default: return launch_replay_t<1, MULTI, false>(a, depth, st);
+    }
+}
+
+static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value,
+                    const int16_t *type, const int16_t *size, const float *X, const float *labels, float *out,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+    EVOGP_REQUIRE(P > 0, "popSize must be larger than 0, got %u", P);
+    EVOGP_REQUIRE(L > 0 && L <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, L);
+    EVOGP_REQUIRE(V > 0 && V <= 1023, "var_len must be in (0, 1023], got %u", V);
+    EVOGP_REQUIRE(O > 0 && O <= 256, "out_len must be in (0, 256], got %u", O);
+    EVOGP_REQUIRE(N > 0, "data_points must be larger than 0, got %u", N);
+    EVOGP_REQUIRE((unsigned long long)P * prog_pitch(L) < (1ull << 40), "population too large");
+    if (workspace_bytes < evogp_eval_workspace_bytes(P, L) || workspace == nullptr) {
+        set_error("workspace too small: need %zu bytes, got %zu", evogp_eval_workspace_bytes(P, L), workspace_bytes);
+        return EVOGP_ERR_WORKSPACE;
+    }
+    int rc = ensure_device_ok();
+    if (rc) return rc;
+    rc = device_props();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace w = carve(workspace, P, L);
+    const int depth = stack_depth_bound((int)L);
+    const bool multi = O > 1;
+    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, depth, st)
+               : launch_lower<false>(w, P, L, V, O, value, type, size, depth, st);
+    if (rc) return rc;
+    ReplayArgs a;
+    a.prog = w.prog; a.sched = w.sched; a.X = X; a.labels = labels; a.out = out;
+    a.P = (int)P; a.Lp = prog_pitch(L); a.N = (int)N; a.V = (int)V; a.O = (int)O;
+    a.NP = 0; a.npass = 0; a.depth = depth; a.mode = mode;
+    return multi ? launch_replay<true>(a, depth, st) : launch_replay<false>(a, depth, st);
+}
+
+}  // namespace evogp
+
+using namespace evogp;
+
+extern "C" size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen) {
+    return 256 + prog_bytes(popSize, maxGPLen);
+}
+
+extern "C" int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
+                              const int16_t *type, const int16_t *subtree_size, const float *variables, float *results,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    return run_eval(MODE_ROWWISE, popSize, 1, maxGPLen, varLen, outLen, value, type, subtree_size, variables, nullptr,
+                    results, workspace, workspace_bytes, stream);
+}
+
+extern "C" int evogp_SR_fitness(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                                int useMSE, const float *value, const int16_t *type, const int16_t *subtree_size,
+                                const float *variables, const float *labels, float *fitnesses, unsigned kernel_type,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    (void)kernel_type;   // reference execute_mode 0..4 (forest.py:340-347): one kernel serves all
+    return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
+                    subtree_size, variables, labels, fitnesses, workspace, workspace_bytes, stream);
+}
+
+extern "C" int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,
+                                   unsigned outLen, const float *value, const int16_t *type,
+                                   const int16_t *subtree_size, const float *variables, float *results,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    return run_eval(MODE_OUTPUT, popSize, dataPoints, gpLen, varLen, outLen, value, type, subtree_size, variables,
+                    nullptr, results, workspace, workspace_bytes, stream);
+}

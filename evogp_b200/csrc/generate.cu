@@ -1,0 +1,217 @@
+// generate.cu — random tree generation into the packed arrays.
+//
+// Replaces generate() (src/evogp/cuda/generate.cu:210-234) and treeGPGenerate
+// (:16-173).  Trees are bit-identical to the reference's for the same `keys`:
+// per-tree taus88 seeded with the reference's FNV-1a hash (kernel.h:157-180), the
+// same draw order, the same roulette scan.
+//
+// What is different is everything around the draws.  The reference keeps a
+// 1024-entry node array plus a 1024-entry frame stack per thread in local memory
+// (12 KB/thread) and writes rows one thread at a time.  Here
+//   * the frame stack is a register: frames on the stack have strictly increasing
+//     depth, so "children still owed at depth d" is a 4-bit field of one 64-bit word;
+//   * nodes are built in shared memory (row pitch odd, so lanes at different
+//     positions rarely collide on a bank);
+//   * subtree sizes need no stack either: scanning the prefix backwards,
+//     size[i] = 1 + size[c1] + size[c2] + ... with c1 = i+1, c2 = c1 + size[c1];
+//   * rows leave the SM through warp-cooperative, coalesced, zero-filled stores.
+#include "common.cuh"
+
+namespace evogp {
+
+// kernel.h:160-172: low 32 bits of 64-bit FNV-1a over the bytes of {n, k1, k2}
+__device__ __forceinline__ uint32_t tree_seed(uint32_t n, uint32_t k1, uint32_t k2) {
+    uint64_t h = 14695981039346656037ULL;
+    const uint32_t a[3] = {n, k1, k2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            h ^= (uint64_t)((a[i] >> (8 * b)) & 0xFFu);
+            h *= 1099511628211ULL;
+        }
+    return (uint32_t)h;
+}
+
+// thrust::random::taus88 (kernel.h:20): three LFSRs, all seeded with the same word
+struct Taus88 {
+    uint32_t z1, z2, z3;
+    __device__ __forceinline__ explicit Taus88(uint32_t s) : z1(s), z2(s), z3(s) {}
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t b;
+        b = ((z1 << 13) ^ z1) >> 19;
+        z1 = ((z1 & 0xFFFFFFFEu) << 12) ^ b;
+        b = ((z2 << 2) ^ z2) >> 25;
+        z2 = ((z2 & 0xFFFFFFF8u) << 4) ^ b;
+        b = ((z3 << 3) ^ z3) >> 11;
+        z3 = ((z3 & 0xFFFFFFF0u) << 17) ^ b;
+        return z1 ^ z2 ^ z3;
+    }
+    // thrust::uniform_real_distribution<float>(0,1): float(u32) / 2^32 (exact scaling; can return 1.0f)
+    __device__ __forceinline__ float uniform() { return __uint2float_rn(next()) * 2.3283064365386963e-10f; }
+};
+
+struct GenArgs {
+    const unsigned *keys;
+    const float *depth2leaf;   // [10]
+    const float *roulette;     // [29]
+    const float *consts;       // [S]
+    float *ovalue;
+    int16_t *otype;
+    int16_t *osize;
+    unsigned P, L, V, O, S;
+    float outProb, constProb;
+    int trees_per_block, pitch;
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
+    extern __shared__ uint32_t gsm[];
+    __shared__ float s_leaf[kMaxFullDepth];
+    __shared__ float s_roul[F_END];
+    const int T = g.trees_per_block, pitch = g.pitch;
+    uint32_t *s_val = gsm;                      // [T][pitch] value bits
+    uint32_t *s_ts = gsm + (size_t)T * pitch;   // [T][pitch] type | size << 16
+    if (threadIdx.x < kMaxFullDepth) s_leaf[threadIdx.x] = g.depth2leaf[threadIdx.x];
+    if (threadIdx.x < F_END) s_roul[threadIdx.x] = g.roulette[threadIdx.x];
+    __syncthreads();
+
+    const unsigned first = blockIdx.x * T;
+    const unsigned n = first + threadIdx.x;
+    int len = 0;
+    if ((int)threadIdx.x < T && n < g.P) {
+        uint32_t *val = s_val + (size_t)threadIdx.x * pitch;
+        uint32_t *ts = s_ts + (size_t)threadIdx.x * pitch;
+        Taus88 rng(tree_seed(n, g.keys[0], g.keys[1]));
+        uint64_t owed = 1;   // 4 bits per depth: children still to generate; root frame {1, 0}
+        int d = 0, cnt = 0;
+        while (d >= 0 && cnt < (int)g.L) {
+            owed -= 1ull << (4 * d);                                   // cd.childs-- (generate.cu:61)
+            const float leafp = d < kMaxFullDepth ? s_leaf[d] : 2.0f;  // reference indexes out of bounds at d >= 10
+            uint32_t vbits;
+            int type, arity = 0;
+            if (rng.uniform() >= leafp) {                              // function node (:71)
+                const float r = rng.uniform();
+                int k = 0;
+                for (int i = F_END - 1; i >= 0; --i)                   // downward roulette scan (:74-84)
+                    if (r >= s_roul[i]) { k = i + 1; break; }
+                type = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
+                arity = type - 1;
+                vbits = __float_as_uint((float)k);
+                if (MULTI) {
+                    if (rng.uniform() <= g.outProb) {                  // output node (:88-96)
+                        const uint32_t oi = rng.next() % g.O;
+                        vbits = ((uint32_t)k & 0xFFFFu) | (oi << 16);  // kernel.h:105-113
+                        type += NT_OUT;
+                    }
+                }
+            } else if (rng.uniform() <= g.constProb) {                 // constant leaf (:109-114)
+                vbits = __float_as_uint(__ldg(g.consts + rng.next() % g.S));
+                type = NT_CONST;
+            } else {                                                   // variable leaf (:116-120)
+                vbits = __float_as_uint((float)(rng.next() % g.V));
+                type = NT_VAR;
+            }
+            val[cnt] = vbits;
+            ts[cnt] = (uint32_t)type & 0xFFFFu;
+            ++cnt;
+            if (arity > 0 && d + 1 < 16) {
+                ++d;
+                owed |= (uint64_t)arity << (4 * d);
+            } else {
+                while (d >= 0 && ((owed >> (4 * d)) & 0xF) == 0) --d;
+            }
+        }
+        // subtree sizes, leaves -> root (:130-158), stack-free
+        for (int i = cnt - 1; i >= 0; --i) {
+            const int t = ts[i] & NT_MASK;
+            const int ar = t <= NT_CONST ? 0 : t - 1;
+            int sz = 1, c = i + 1;
+            for (int k = 0; k < ar; ++k) {
+                const int cs = c < cnt ? (int)(ts[c] >> 16) : 0;
+                sz += cs;
+                c += cs;
+            }
+            ts[i] |= (uint32_t)sz << 16;
+        }
+        len = cnt > 0 ? (int)(ts[0] >> 16) : 0;
+        if (cnt < pitch) ts[cnt] = 0;
+        // remember the valid length in the padding word of the row (pitch > L always)
+        val[pitch - 1] = (uint32_t)len;
+    }
+    __syncthreads();
+
+    // cooperative, coalesced, zero-filled write-out: one warp per row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int L = (int)g.L;
+    for (int r = warp; r < T; r += nwarp) {
+        const unsigned row = first + r;
+        if (row >= g.P) break;
+        const uint32_t *val = s_val + (size_t)r * pitch;
+        const uint32_t *ts = s_ts + (size_t)r * pitch;
+        const int rl = (int)val[pitch - 1];
+        float *ov = g.ovalue + (size_t)row * L;
+        int16_t *ot = g.otype + (size_t)row * L;
+        int16_t *os = g.osize + (size_t)row * L;
+        if ((L & 1) == 0) {
+            for (int j = lane * 2; j < L; j += 64) {
+                const uint32_t v0 = j < rl ? val[j] : 0u, v1 = j + 1 < rl ? val[j + 1] : 0u;
+                const uint32_t a0 = j < rl ? ts[j] : 0u, a1 = j + 1 < rl ? ts[j + 1] : 0u;
+                *reinterpret_cast<uint2 *>(ov + j) = make_uint2(v0, v1);
+                *reinterpret_cast<uint32_t *>(ot + j) = (a0 & 0xFFFFu) | (a1 << 16);
+                *reinterpret_cast<uint32_t *>(os + j) = (a0 >> 16) | (a1 & 0xFFFF0000u);
+            }
+        } else {
+            for (int j = lane; j < L; j += 32) {
+                const uint32_t v = j < rl ? val[j] : 0u, a = j < rl ? ts[j] : 0u;
+                ov[j] = __uint_as_float(v);
+                ot[j] = (int16_t)(a & 0xFFFFu);
+                os[j] = (int16_t)(a >> 16);
+            }
+        }
+    }
+}
+
+}  // namespace evogp
+
+using namespace evogp;
+
+extern "C" int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
+                              unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
+                              const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
+                              float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream) {
+    // torch_wrapper.cu:48-54
+    EVOGP_REQUIRE(popSize > 0, "pop_size must be larger than 0, got %u", popSize);
+    EVOGP_REQUIRE(maxGPLen > 0 && maxGPLen <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, maxGPLen);
+    EVOGP_REQUIRE(varLen > 0, "var_len must be larger than 0, got %u", varLen);
+    EVOGP_REQUIRE(outLen > 0, "out_len must be larger than 0, got %u", outLen);
+    EVOGP_REQUIRE(constSamplesLen > 0, "const_samples_len must be larger than 0, got %u", constSamplesLen);
+    EVOGP_REQUIRE(outProb >= 0.f && outProb <= 1.f, "out_prob must be in [0, 1], got %f", outProb);
+    EVOGP_REQUIRE(constProb >= 0.f && constProb <= 1.f, "const_prob must be in [0, 1], got %f", constProb);
+    int rc = ensure_device_ok();
+    if (rc) return rc;
+    GenArgs a;
+    a.keys = keys; a.depth2leaf = depth2leafProbs; a.roulette = rouletteFuncs; a.consts = constSamples;
+    a.ovalue = value_res; a.otype = type_res; a.osize = subtree_size_res;
+    a.P = popSize; a.L = maxGPLen; a.V = varLen; a.O = outLen; a.S = constSamplesLen;
+    a.outProb = outProb; a.constProb = constProb;
+    a.pitch = (int)(maxGPLen | 1u) + ((maxGPLen & 1u) ? 2 : 0);   // odd and > L
+    const size_t per_tree = (size_t)a.pitch * 8;
+    int T = (int)((192 * 1024) / per_tree);
+    if (T > 128) T = 128;
+    if (T < 1) T = 1;
+    a.trees_per_block = T;
+    const int threads = ((T + 31) / 32) * 32;
+    const size_t smem = per_tree * T;
+    const unsigned grid = (popSize + T - 1) / T;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (outLen > 1) {
+        EVOGP_CUDA(cudaFuncSetAttribute(generate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        generate_kernel<true><<<grid, threads, smem, st>>>(a);
+    } else {
+        EVOGP_CUDA(cudaFuncSetAttribute(generate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        generate_kernel<false><<<grid, threads, smem, st>>>(a);
+    }
+    count_launch();
+    return check_launch("generate");
+}

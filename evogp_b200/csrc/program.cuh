@@ -1,0 +1,124 @@
+// program.cuh — the accumulator-machine program a packed tree row is lowered to,
+// and the scalar operator definitions shared by the lowering pass (which never
+// evaluates them) and the replay kernels.
+//
+// Why a lowering pass at all: the reference interprets the prefix row once per
+// (tree, datapoint) thread with a private operand stack in local memory
+// (forward.cu:246-302).  Here one warp replays a tree over 32*K datapoints per
+// pass, so control flow is warp-uniform and the only question is how many issue
+// slots a node costs.  Lowering removes every leaf push (leaves become operands of
+// their parent), orders sibling subtrees Sethi-Ullman style so the operand stack
+// never holds more than ~log2(L) live vectors (it lives in shared memory, one
+// float4 column per lane), and turns each function node into ONE instruction whose
+// case label already says where its operands are.
+//
+// Values computed per node are exactly the reference's: reordering sibling
+// evaluation does not change any operand of any operator.
+#pragma once
+#include "common.cuh"
+
+namespace evogp {
+
+// ---------------------------------------------------------------------------
+// instruction word (8 bytes): {header, constant}
+//   header [7:0]   opcode (see below)
+//          [8]     PUSH    spill acc to the operand stack before executing
+//          [9]     A_CONST leaf operand A is the constant in .y (else variable idxA)
+//          [10]    B_CONST leaf operand B is the constant in .y (else variable idxB)
+//          [11]    OUT     multi-output node: add result to outs[idxB], forward
+//                          the right-most child's value instead (forward.cu:236-242)
+//          [21:12] idxA    variable index of leaf A  (C_IF: operand permutation)
+//          [31:22] idxB    variable index of leaf B / output index when OUT
+// At most one operand of an instruction is a constant; the lowering pass inserts
+// a C_LOAD when a node has two constant leaves.
+// ---------------------------------------------------------------------------
+constexpr uint32_t I_PUSH = 1u << 8, I_ACONST = 1u << 9, I_BCONST = 1u << 10, I_OUT = 1u << 11;
+constexpr int I_IDXA_SHIFT = 12, I_IDXB_SHIFT = 22;
+constexpr uint32_t I_IDX_MASK = 0x3FFu;
+
+constexpr int NUM_U = 16;  // 15 unary functions (ids 14..28) + "unknown id -> 0"
+constexpr int NUM_B = 14;  // 13 binary functions (ids 1..13) + "unknown id -> 0"
+constexpr int U_ZERO = 15, B_ZERO = 13;
+
+enum : int {
+    C_END = 0,   // stop
+    C_LOAD = 1,  // acc = leafA
+    C_IF = 2,    // acc = a > 0 ? b : c; operands are acc / stack top / stack top-1 per idxA
+    C_NAN = 3,   // malformed row: acc = NaN
+    C_UA = 8,                // acc = u(acc)
+    C_UL = C_UA + NUM_U,     // acc = u(leafA)
+    C_AL = C_UL + NUM_U,     // acc = b(acc, leafA)
+    C_LA = C_AL + NUM_B,     // acc = b(leafA, acc)
+    C_LL = C_LA + NUM_B,     // acc = b(leafA, leafB)
+    C_SA = C_LL + NUM_B,     // acc = b(pop, acc)
+    C_AS = C_SA + NUM_B,     // acc = b(acc, pop)
+    C_COUNT = C_AS + NUM_B
+};
+
+__host__ __device__ inline int unary_slot(unsigned f) { return (f >= (unsigned)F_SIN && f < (unsigned)F_END) ? (int)f - F_SIN : U_ZERO; }
+__host__ __device__ inline int binary_slot(unsigned f) { return (f >= (unsigned)F_ADD && f <= (unsigned)F_GE) ? (int)f - F_ADD : B_ZERO; }
+
+// Upper bound of the operand-stack depth any well-formed row of `len` nodes can need
+// after Sethi-Ullman ordering.  M(d) = fewest nodes of a subtree needing >= d slots:
+// a ternary of three leaves already needs 2 (4 nodes); beyond that the cheapest way
+// to need d is a binary node over two subtrees needing d-1: M(d) = 1 + 2 M(d-1).
+__host__ __device__ inline int stack_depth_bound(int len) {
+    int d = 2, m = 4;
+    if (len < 4) return 1;
+    while (1 + 2 * m <= len) {
+        m = 1 + 2 * m;
+        d++;
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// operator semantics — forward.cu:125-224, compiled like the reference with
+// -use_fast_math (setup.py:55) so every intrinsic lowers identically
+// (div.approx.ftz, sin/cos.approx, ex2/lg2.approx, tanh.approx, sqrt.approx).
+// ---------------------------------------------------------------------------
+template <int U>
+__device__ __forceinline__ float unary_op(float a) {
+    if constexpr (U == F_SIN - F_SIN) return sinf(a);
+    else if constexpr (U == F_COS - F_SIN) return cosf(a);
+    else if constexpr (U == F_TAN - F_SIN) return tanf(a);
+    else if constexpr (U == F_SINH - F_SIN) return sinhf(a);
+    else if constexpr (U == F_COSH - F_SIN) return coshf(a);
+    else if constexpr (U == F_TANH - F_SIN) return tanhf(a);
+    else if constexpr (U == F_LOG - F_SIN) return logf(a);
+    else if constexpr (U == F_LOOSE_LOG - F_SIN) return a == 0.0f ? -kMaxVal : logf(fabsf(a));
+    else if constexpr (U == F_EXP - F_SIN) return expf(a);
+    else if constexpr (U == F_INV - F_SIN) return a == 0.0f ? __int_as_float(0x7fffffff) : 1.0f / a;
+    else if constexpr (U == F_LOOSE_INV - F_SIN) {
+        if (fabsf(a) <= kDelta) a = copysignf(kDelta, a);
+        return 1.0f / a;
+    } else if constexpr (U == F_NEG - F_SIN) return -a;
+    else if constexpr (U == F_ABS - F_SIN) return fabsf(a);
+    else if constexpr (U == F_SQRT - F_SIN) return sqrtf(a);
+    else if constexpr (U == F_LOOSE_SQRT - F_SIN) {
+        if (a <= 0.0f) a = fabsf(a);
+        return sqrtf(a);
+    } else return 0.0f;
+}
+
+template <int B>
+__device__ __forceinline__ float binary_op(float a, float b) {
+    if constexpr (B == F_ADD - F_ADD) return __fadd_rn(a, b);   // _rn: never contracted with a neighbour
+    else if constexpr (B == F_SUB - F_ADD) return __fsub_rn(a, b);
+    else if constexpr (B == F_MUL - F_ADD) return __fmul_rn(a, b);
+    else if constexpr (B == F_DIV - F_ADD) return b == 0.0f ? __int_as_float(0x7fffffff) : a / b;
+    else if constexpr (B == F_LOOSE_DIV - F_ADD) {
+        if (fabsf(b) <= kDelta) b = copysignf(kDelta, b);
+        return a / b;
+    } else if constexpr (B == F_POW - F_ADD) return powf(a, b);
+    else if constexpr (B == F_LOOSE_POW - F_ADD) return (a == 0.0f && b == 0.0f) ? 0.0f : powf(fabsf(a), b);
+    else if constexpr (B == F_MAX - F_ADD) return a >= b ? a : b;
+    else if constexpr (B == F_MIN - F_ADD) return a <= b ? a : b;
+    else if constexpr (B == F_LT - F_ADD) return a < b ? 1.0f : -1.0f;
+    else if constexpr (B == F_GT - F_ADD) return a > b ? 1.0f : -1.0f;
+    else if constexpr (B == F_LE - F_ADD) return a <= b ? 1.0f : -1.0f;
+    else if constexpr (B == F_GE - F_ADD) return a >= b ? 1.0f : -1.0f;
+    else return 0.0f;
+}
+
+}  // namespace evogp

@@ -1,0 +1,3 @@
+from .base import BaseProblem  # noqa: F401
+from .symbolic_regression import SymbolicRegression  # noqa: F401
+from .classification import Classification  # noqa: F401

@@ -1,0 +1,114 @@
+/*
+ * evogp_b200.h — C ABI of the B200-native EvoGP hot path (libevogp_b200.so).
+ *
+ * Drop-in boundary.  The reference's FFI for this path is the torch operator
+ * library `evogp_cuda` (src/evogp/cuda/torch_wrapper.cu:291-307) sitting on
+ * five plain host functions that take raw device pointers
+ * (src/evogp/cuda/kernel.h:23-97).  The entry points below are those five
+ * functions — same argument order and meaning — as `extern "C"` symbols, with
+ * three additions the reference lacks: an explicit CUDA stream, an int status
+ * (0 = ok, else see evogp_last_error()), and caller-provided scratch for the
+ * fitness evaluator.  evogp_b200/csrc/torch_ops.cpp re-registers the same five
+ * `evogp_cuda::tree_*` schemas on top of them.
+ *
+ * All pointers are DEVICE pointers unless the function name ends in `_host`.
+ * Inputs are borrowed and never written; outputs must be preallocated by the
+ * caller ([P, L] arrays are row-major, contiguous).  Calls are asynchronous on
+ * `stream` (a cudaStream_t; NULL = legacy default stream).  There is no CPU
+ * fallback: every call fails with EVOGP_ERR_CUDA when no sm_100 device is
+ * usable.
+ *
+ * Packed forest layout (reference: src/evogp/tree/forest.py:13-40,
+ * src/evogp/cuda/defs.h:10-22): three [P, L] arrays, one tree per row in
+ * prefix order; node_value f32, node_type i16, subtree_size i16; valid prefix
+ * length = subtree_size[i, 0].  Unlike the reference (which leaves row tails
+ * uninitialised), every producer here zero-fills the tail.
+ */
+#ifndef EVOGP_B200_H
+#define EVOGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVOGP_MAX_STACK 1024      /* defs.h:5  — upper bound of max_tree_len   */
+#define EVOGP_MAX_FULL_DEPTH 10   /* defs.h:5  — length of depth2leaf_probs    */
+#define EVOGP_FUNC_END 29         /* defs.h:56 — length of roulette_funcs      */
+
+enum {
+    EVOGP_OK = 0,
+    EVOGP_ERR_ARG = 1,        /* scalar argument out of range (torch_wrapper.cu:48-60 checks) */
+    EVOGP_ERR_CUDA = 2,       /* launch / runtime failure, or no usable device              */
+    EVOGP_ERR_WORKSPACE = 3,  /* scratch buffer too small                                   */
+    EVOGP_ERR_UNSUPPORTED = 4 /* shape beyond what the kernels stage in shared memory       */
+};
+
+/* Library identity / diagnostics. */
+int evogp_version(void);
+const char *evogp_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+unsigned long long evogp_launch_count(void);
+
+/* replaces generate(), kernel.h:23-38 (generate.cu:210-234).  keys: uint32[2];
+ * depth2leafProbs: f32[10]; rouletteFuncs: f32[29] cumulative; constSamples: f32[constSamplesLen].
+ * RNG: taus88 seeded with hash(n, keys[0], keys[1]) — bit-identical trees to the reference. */
+int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, unsigned constSamplesLen,
+                   float outProb, float constProb, const unsigned *keys, const float *depth2leafProbs,
+                   const float *rouletteFuncs, const float *constSamples, float *value_res, int16_t *type_res,
+                   int16_t *subtree_size_res, void *stream);
+
+/* replaces mutate(), kernel.h:40-53 (mutation.cu:186-219). */
+int evogp_mutate(int popSize, int gpLen, const float *value_ori, const int16_t *type_ori,
+                 const int16_t *subtree_size_ori, const int *mutateIndices, const float *value_new,
+                 const int16_t *type_new, const int16_t *subtree_size_new, float *value_res, int16_t *type_res,
+                 int16_t *subtree_size_res, void *stream);
+
+/* replaces crossover(), kernel.h:55-69 (mutation.cu:312-347). */
+int evogp_crossover(int pop_size_ori, int pop_size_new, int gpLen, const float *value_ori, const int16_t *type_ori,
+                    const int16_t *subtree_size_ori, const int *left_idx, const int *right_idx,
+                    const int *left_node_idx, const int *right_node_idx, float *value_res, int16_t *type_res,
+                    int16_t *subtree_size_res, void *stream);
+
+/* Scratch needed by evogp_evaluate / evogp_SR_fitness / evogp_batch_forward for a
+ * population of popSize rows of width maxGPLen (compiled programs + scheduler words). */
+size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen);
+
+/* replaces evaluate(), kernel.h:71-81 (forward.cu:353-371): tree n on variables[n, :] -> results[n, :outLen]. */
+int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
+                   const int16_t *type, const int16_t *subtree_size, const float *variables, float *results,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* replaces SR_fitness(), kernel.h:83-97 (forward.cu:827-856).
+ * fitnesses[i] = (1/dataPoints) * sum_n sum_o loss(labels[n,o] - out_o(tree_i, variables[n,:])),
+ * loss = square (useMSE) or abs.  kernel_type (the reference's execute_mode code 0..4) is accepted
+ * and ignored: one kernel serves every mode. */
+int evogp_SR_fitness(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                     int useMSE, const float *value, const int16_t *type, const int16_t *subtree_size,
+                     const float *variables, const float *labels, float *fitnesses, unsigned kernel_type,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused form of Forest.batch_forward (tree/forest.py:143-176), which the reference
+ * implements by replicating the forest dataPoints times: results[P, N, O]. */
+int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                        const float *value, const int16_t *type, const int16_t *subtree_size,
+                        const float *variables, float *results, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* Host-buffer form of evogp_SR_fitness: every pointer is HOST memory (pinned memory
+ * makes the copies asynchronous).  Uploads the forest in row chunks on two streams so
+ * H2D overlaps evaluation, downloads fitnesses[popSize], and returns after the result
+ * is on the host.  Device staging buffers are cached inside the library.  device = CUDA
+ * device ordinal. */
+int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                          int useMSE, const float *value, const int16_t *type, const int16_t *subtree_size,
+                          const float *variables, const float *labels, float *fitnesses, int device);
+/* Free the cached staging buffers of evogp_SR_fitness_host. */
+void evogp_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOGP_B200_H */
