@@ -197,41 +197,39 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                 const float cst = __uint_as_float(ins.y);
                 ++pc;
                 ins = prog[pc < g.Lp ? pc : g.Lp - 1];   // prefetch the next slot
-                if (w & I_PUSH) {
-                    st_vec<K>(stack + sp * SLOT + lane_off, acc);
-                    ++sp;
+                if constexpr (!MULTI) {   // multi-output programs have no operand stack
+                    if (w & I_PUSH) {
+                        st_vec<K>(stack + sp * SLOT + lane_off, acc);
+                        ++sp;
+                    }
                 }
                 const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
 
-// result r, forwarded value `right` (only used by multi-output nodes)
-#define FINISH(r, right)                                                          \
+// result r of a function node.  Multi-output programs (lower_tree_multi) consist of OUT
+// instructions only: the result is added to outs[idxB]; nothing consumes acc afterwards
+// except the C_LOAD -> C_AL pair of a binary node.
+#define FINISH(r)                                                                 \
     if constexpr (MULTI) {                                                        \
-        if (w & I_OUT) {                                                          \
-            if (ib != I_IDX_MASK) {                                               \
-                float o_[K];                                                      \
-                ld_vec<K>(o_, outs + ib * SLOT + lane_off);                       \
-                FOR_K o_[k] += r[k];                                              \
-                st_vec<K>(outs + ib * SLOT + lane_off, o_);                       \
-            }                                                                     \
-            FOR_K acc[k] = right[k];                                              \
-        } else {                                                                  \
-            FOR_K acc[k] = r[k];                                                  \
+        if ((w & I_OUT) && ib != I_IDX_MASK) {                                    \
+            float o_[K];                                                          \
+            ld_vec<K>(o_, outs + ib * SLOT + lane_off);                           \
+            FOR_K o_[k] += r[k];                                                  \
+            st_vec<K>(outs + ib * SLOT + lane_off, o_);                           \
         }                                                                         \
-    } else {                                                                      \
-        FOR_K acc[k] = r[k];                                                      \
-    }
+    }                                                                             \
+    FOR_K acc[k] = r[k];
 
 #define CASE_U(u)                                                                 \
     case C_UA + u: {                                                              \
         float r[K];                                                               \
         FOR_K r[k] = unary_op<u>(acc[k]);                                         \
-        FINISH(r, acc)                                                            \
+        FINISH(r)                                                            \
     } break;                                                                      \
     case C_UL + u: {                                                              \
         float l[K], r[K];                                                         \
         fetch(l, w & I_ACONST, cst, ia);                                          \
         FOR_K r[k] = unary_op<u>(l[k]);                                           \
-        FINISH(r, l)                                                              \
+        FINISH(r)                                                              \
     } break;
 
 #define CASE_B(b)                                                                 \
@@ -239,13 +237,13 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
         float l[K], r[K];                                                         \
         fetch(l, w & I_ACONST, cst, ia);                                          \
         FOR_K r[k] = binary_op<b>(acc[k], l[k]);                                  \
-        FINISH(r, l)                                                              \
+        FINISH(r)                                                              \
     } break;                                                                      \
     case C_LA + b: {                                                              \
         float l[K], r[K];                                                         \
         fetch(l, w & I_ACONST, cst, ia);                                          \
         FOR_K r[k] = binary_op<b>(l[k], acc[k]);                                  \
-        FINISH(r, acc)                                                            \
+        FINISH(r)                                                            \
     } break;                                                                      \
     case C_LL + b: {                                                              \
         float l[K], m[K];                                                         \
@@ -258,20 +256,37 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
         --sp;                                                                     \
         ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
         FOR_K r[k] = binary_op<b>(s[k], acc[k]);                                  \
-        FINISH(r, acc)                                                            \
+        FINISH(r)                                                            \
     } break;                                                                      \
     case C_AS + b: {                                                              \
         float s[K], r[K];                                                         \
         --sp;                                                                     \
         ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
         FOR_K r[k] = binary_op<b>(acc[k], s[k]);                                  \
-        FINISH(r, s)                                                              \
+        FINISH(r)                                                              \
     } break;
 
                 switch (w & 0xFFu) {
                 case C_END: goto tree_done;
                 case C_LOAD: fetch(acc, w & I_ACONST, cst, ia); break;
-                case C_NAN: { FOR_K acc[k] = __int_as_float(0x7fc00000); } break;
+                case C_NAN: {
+                    FOR_K acc[k] = __int_as_float(0x7fc00000);
+                    if constexpr (MULTI)
+                        for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
+                } break;
+                case C_IF3: {
+                    if constexpr (MULTI) {   // {hdr, a}{b, c}: three leaf operands
+                        float a[K], b[K], c[K], r[K];
+                        const uint2 ext = ins;           // second slot (already prefetched)
+                        ++pc;
+                        ins = prog[pc < g.Lp ? pc : g.Lp - 1];
+                        fetch(a, w & I_ACONST, cst, ia);
+                        fetch(b, w & I_IF3_BCONST, __uint_as_float(ext.x), ext.x & I_IDX_MASK);
+                        fetch(c, w & I_IF3_CCONST, __uint_as_float(ext.y), ext.y & I_IDX_MASK);
+                        FOR_K r[k] = a[k] > 0.0f ? b[k] : c[k];
+                        FINISH(r)
+                    }
+                } break;
                 case C_IF: {
                     float t1[K], t2[K], a[K], b[K], c[K], r[K];
                     sp -= 2;
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                         c[k] = sc == 0 ? acc[k] : (sc == 1 ? t1[k] : t2[k]);
                         r[k] = a[k] > 0.0f ? b[k] : c[k];   // forward.cu:223
                     }
-                    FINISH(r, c)
+                    FINISH(r)
                 } break;
                     CASE_U(0) CASE_U(1) CASE_U(2) CASE_U(3) CASE_U(4) CASE_U(5) CASE_U(6) CASE_U(7)
                     CASE_U(8) CASE_U(9) CASE_U(10) CASE_U(11) CASE_U(12) CASE_U(13) CASE_U(14) CASE_U(15)
@@ -355,6 +370,8 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
 // host side
 // ---------------------------------------------------------------------------
 static int g_sm_count = 0, g_max_smem = 0;
+// optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
+static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
 
 static int device_props() {
     if (g_sm_count) return EVOGP_OK;
@@ -441,7 +458,9 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     long long want = ((long long)a.P + warps - 1) / warps;
     int grid = (int)(want < (long long)per_sm * g_sm_count ? want : (long long)per_sm * g_sm_count);
     if (grid < 1) grid = 1;
+    if (g_ev_replay_begin) cudaEventRecord(g_ev_replay_begin, st);
     kern<<<grid, warps * 32, smem, st>>>(a);
+    if (g_ev_replay_end) cudaEventRecord(g_ev_replay_end, st);
     count_launch();
     return check_launch("replay_kernel");
 }
@@ -477,6 +496,7 @@ static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, un
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
+    EVOGP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));   // ticket counter + diagnostics words
     rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, depth, st)
                : launch_lower<false>(w, P, L, V, O, value, type, size, depth, st);
     if (rc) return rc;
@@ -490,6 +510,11 @@ static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, un
 }  // namespace evogp
 
 using namespace evogp;
+
+extern "C" void evogp_eval_set_timing_events(void *begin_event, void *end_event) {
+    g_ev_replay_begin = static_cast<cudaEvent_t>(begin_event);
+    g_ev_replay_end = static_cast<cudaEvent_t>(end_event);
+}
 
 extern "C" size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen) {
     return 256 + prog_bytes(popSize, maxGPLen);

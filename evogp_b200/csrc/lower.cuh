@@ -6,82 +6,114 @@
 // Structure is derived exactly the way the reference's evaluator derives it
 // (forward.cu:277-296): from node types and subtree_size[0] only; interior
 // subtree_size entries are recomputed, not trusted.
+//
+// lower_tree() is __host__ __device__ so that tests/host_lower_harness.cu can run the
+// very same code on the CPU and replay its output against the oracle.
 #pragma once
 #include "program.cuh"
 
+#include <cstring>
+#ifdef __CUDA_ARCH__
+#define EVOGP_LDG(p) __ldg(p)
+#else
+#define EVOGP_LDG(p) (*(p))
+#endif
+
 namespace evogp {
 
+__host__ __device__ __forceinline__ uint32_t f32_bits(float x) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(x);
+#else
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    return u;
+#endif
+}
+// cvt.rzi.u32.f32 / cvt.rzi.s32.f32 semantics (saturating, NaN -> 0) on both sides
+__host__ __device__ __forceinline__ unsigned f32_to_u32(float v) {
+#ifdef __CUDA_ARCH__
+    return __float2uint_rz(v);
+#else
+    if (!(v > 0.0f)) return 0u;
+    return v >= 4294967296.0f ? 0xFFFFFFFFu : (unsigned)v;
+#endif
+}
+__host__ __device__ __forceinline__ int f32_to_i32(float v) {
+#ifdef __CUDA_ARCH__
+    return __float2int_rz(v);
+#else
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return -2147483647 - 1;
+    return (int)v;
+#endif
+}
+__host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
 // scratch word A: subtree size [0:11) | instruction slots [11:22) | stack need [22:30) | complex [31]
-__device__ __forceinline__ uint32_t packA(int sz, int ni, int need, int cplx) {
+__host__ __device__ __forceinline__ uint32_t packA(int sz, int ni, int need, int cplx) {
     return (uint32_t)sz | ((uint32_t)ni << 11) | ((uint32_t)need << 22) | ((uint32_t)cplx << 31);
 }
-__device__ __forceinline__ int a_sz(uint32_t a) { return a & 0x7FF; }
-__device__ __forceinline__ int a_ni(uint32_t a) { return (a >> 11) & 0x7FF; }
-__device__ __forceinline__ int a_need(uint32_t a) { return (a >> 22) & 0xFF; }
-__device__ __forceinline__ int a_cplx(uint32_t a) { return a >> 31; }
+__host__ __device__ __forceinline__ int a_sz(uint32_t a) { return a & 0x7FF; }
+__host__ __device__ __forceinline__ int a_ni(uint32_t a) { return (a >> 11) & 0x7FF; }
+__host__ __device__ __forceinline__ int a_need(uint32_t a) { return (a >> 22) & 0xFF; }
+__host__ __device__ __forceinline__ int a_cplx(uint32_t a) { return a >> 31; }
 
 template <bool MULTI>
-__device__ __forceinline__ int node_arity(int t) {
+__host__ __device__ __forceinline__ int node_arity(int t) {
     if (MULTI) t &= NT_MASK;   // single-output mode does not mask (forward.cu:91-94)
     return (t == NT_VAR || t == NT_CONST) ? 0 : (t == NT_UFUNC ? 1 : (t == NT_BFUNC ? 2 : 3));
 }
 
 // leaf operand descriptor for slot A (shift 12 / flag A_CONST) or B (shift 22 / B_CONST)
-__device__ __forceinline__ void leaf_desc(int t, float v, int V, bool slotB, uint32_t &hdr, uint32_t &cst) {
+__host__ __device__ __forceinline__ void leaf_desc(int t, float v, int V, bool slotB, uint32_t &hdr, uint32_t &cst) {
     if ((t & NT_MASK) == NT_CONST) {
         hdr |= slotB ? I_BCONST : I_ACONST;
-        cst = __float_as_uint(v);
+        cst = f32_bits(v);
     } else {
-        int idx = (int)v;                      // forward.cu:100 `(int)node_value`
+        int idx = f32_to_i32(v);               // forward.cu:100 `(int)node_value`
         idx = idx < 0 ? 0 : (idx >= V ? V - 1 : idx);   // reference reads out of bounds here; clamp
         hdr |= (uint32_t)idx << (slotB ? I_IDXB_SHIFT : I_IDXA_SHIFT);
     }
 }
 
-struct LowerArgs {
-    const float *value;
-    const int16_t *type;
-    const int16_t *size;
-    uint2 *prog;        // [P][Lp]
-    unsigned *sched;    // scheduler words (zeroed here for the replay kernel)
-    unsigned *flags;    // [0]: count of malformed rows, [1]: max stack need seen
-    int P, L, Lp, V, O, depth_budget;
-};
+__host__ __device__ __forceinline__ uint2 mk2(uint32_t a, uint32_t b) {
+    uint2 r;
+    r.x = a;
+    r.y = b;
+    return r;
+}
 
-template <bool MULTI>
-__global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
-    extern __shared__ uint32_t scratch[];
-    const int T = blockDim.x, tid = threadIdx.x;
-    uint32_t *SA = scratch;               // [L][T]
-    uint32_t *SB = scratch + g.L * T;     // [L][T]: start [0:11) | live [11]
-    const int n = blockIdx.x * T + tid;
-    if (blockIdx.x == 0 && tid < 4) g.sched[tid] = 0;
-    if (n >= g.P) return;
-
-    const float *val = g.value + (size_t)n * g.L;
-    const int16_t *typ = g.type + (size_t)n * g.L;
-    uint2 *out = g.prog + (size_t)n * g.Lp;
-    int len = g.size[(size_t)n * g.L];
-    bool bad = len < 1 || len > g.L;
+// Lowers one row.  SA/SB: two scratch arrays of `len` words, element i at [i * stride].
+// Returns the operand-stack need of the program, or -1 for a malformed row (the program
+// is then {C_NAN, C_END}).
+__host__ __device__ inline int lower_tree_single(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
+                                          int depth_budget, uint2 *out, uint32_t *SA, uint32_t *SB, int stride) {
+    bool bad = len < 1 || len > L;
     if (bad) len = 0;
 
     // ---- pass A: leaves -> root.  size, slot count, Sethi-Ullman need per subtree ----
     for (int i = len - 1; i >= 0 && !bad; --i) {
-        const int t = __ldg(typ + i);
-        const int ar = node_arity<MULTI>(t);
+        const int t = EVOGP_LDG(typ + i);
+        const int ar = node_arity<false>(t);
         if (ar == 0) {
-            SA[i * T + tid] = packA(1, 0, 0, 0);
+            SA[i * stride] = packA(1, 0, 0, 0);
             continue;
         }
         int c = i + 1, sz = 1;
-        uint32_t ch[3];
+        uint32_t ch[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (k < ar) {
-                if (c >= len) { bad = true; break; }
-                ch[k] = SA[c * T + tid];
-                c += a_sz(ch[k]);
-                sz += a_sz(ch[k]);
+            if (k < ar && !bad) {
+                if (c >= len) {
+                    bad = true;
+                } else {
+                    ch[k] = SA[c * stride];
+                    c += a_sz(ch[k]);
+                    sz += a_sz(ch[k]);
+                }
             }
         }
         if (bad) break;
@@ -92,14 +124,14 @@ __global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
         } else if (ar == 2) {
             const int cx = a_cplx(ch[0]), cy = a_cplx(ch[1]);
             if (!cx && !cy) {
-                const bool both_const = (__ldg(typ + i + 1) & NT_MASK) == NT_CONST && (__ldg(typ + i + 2) & NT_MASK) == NT_CONST;
-                const bool is_out = MULTI && (t & NT_OUT);
-                ni = (both_const || is_out) ? 2 : 1;
+                const bool both_const = (EVOGP_LDG(typ + i + 1) & NT_MASK) == NT_CONST &&
+                                        (EVOGP_LDG(typ + i + 2) & NT_MASK) == NT_CONST;
+                ni = both_const ? 2 : 1;
                 need = 0;
             } else if (cx && cy) {
                 const int nx = a_need(ch[0]), ny = a_need(ch[1]);
                 ni = a_ni(ch[0]) + a_ni(ch[1]) + 1;
-                need = max(max(nx, ny), min(nx, ny) + 1);
+                need = imax(imax(nx, ny), imin(nx, ny) + 1);
             } else {
                 const uint32_t cc = cx ? ch[0] : ch[1];
                 ni = a_ni(cc) + 1;
@@ -113,106 +145,99 @@ __global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
                 nd[k] = a_cplx(ch[k]) ? a_need(ch[k]) : 0;
                 tot += a_cplx(ch[k]) ? a_ni(ch[k]) : 1;
             }
-            int hi = max(nd[0], max(nd[1], nd[2])), lo = min(nd[0], min(nd[1], nd[2]));
-            int mid = nd[0] + nd[1] + nd[2] - hi - lo;
+            const int hi = imax(nd[0], imax(nd[1], nd[2])), lo = imin(nd[0], imin(nd[1], nd[2]));
+            const int mid = nd[0] + nd[1] + nd[2] - hi - lo;
             ni = tot;
-            need = max(hi, max(mid + 1, lo + 2));
+            need = imax(hi, imax(mid + 1, lo + 2));
         }
-        SA[i * T + tid] = packA(sz, ni, need, 1);
+        SA[i * stride] = packA(sz, ni, need, 1);
     }
+    int root_need = 0;
     if (!bad && len > 0) {
-        const uint32_t r = SA[tid];
-        if (a_sz(r) != len) bad = true;                          // prefix does not close at len
-        else if (a_need(r) > g.depth_budget) bad = true;         // cannot happen (stack_depth_bound)
-        else atomicMax(g.flags + 1, (unsigned)a_need(r));
+        const uint32_t r = SA[0];
+        root_need = a_cplx(r) ? a_need(r) : 0;
+        if (a_sz(r) != len) bad = true;                  // prefix does not close at len
+        else if (root_need > depth_budget) bad = true;   // cannot happen (stack_depth_bound)
     }
-    if (bad) {
-        out[0] = make_uint2(C_NAN, 0);
-        if (g.Lp > 1) out[1] = make_uint2(C_END, 0);
-        atomicAdd(g.flags, 1u);
-        return;
+    if (bad || len == 0) {
+        out[0] = mk2(C_NAN, 0);
+        if (Lp > 1) out[1] = mk2(C_END, 0);
+        return -1;
     }
 
     // ---- pass B: root -> leaves.  place each subtree's slot range, emit instructions ----
     {
-        const uint32_t r = SA[tid];
+        const uint32_t r = SA[0];
         if (!a_cplx(r)) {   // the tree is a single leaf
             uint32_t hdr = C_LOAD, cst = 0;
-            leaf_desc(__ldg(typ), __ldg(val), g.V, false, hdr, cst);
-            out[0] = make_uint2(hdr, cst);
-            if (g.Lp > 1) out[1] = make_uint2(C_END, 0);
-            return;
+            leaf_desc(EVOGP_LDG(typ), EVOGP_LDG(val), V, false, hdr, cst);
+            out[0] = mk2(hdr, cst);
+            if (Lp > 1) out[1] = mk2(C_END, 0);
+            return 0;
         }
-        SB[tid] = 0;   // root: start 0, acc not live
-        if (a_ni(r) < g.Lp) out[a_ni(r)] = make_uint2(C_END, 0);
+        SB[0] = 0;   // root: start 0, acc not live
+        if (a_ni(r) < Lp) out[a_ni(r)] = mk2(C_END, 0);
     }
     for (int i = 0; i < len; ++i) {
-        const uint32_t me = SA[i * T + tid];
+        const uint32_t me = SA[i * stride];
         if (!a_cplx(me)) continue;
-        const uint32_t sb = SB[i * T + tid];
+        const uint32_t sb = SB[i * stride];
         const int st = sb & 0x7FF;
-        const uint32_t live_push = (sb >> 11) & 1 ? I_PUSH : 0;
+        const uint32_t live_push = ((sb >> 11) & 1) ? I_PUSH : 0;
         const int own = st + a_ni(me) - 1;
-        const int t = __ldg(typ + i);
-        const float v = __ldg(val + i);
-        const int ar = node_arity<MULTI>(t);
-        const bool is_out = MULTI && (t & NT_OUT);
-        unsigned func = (unsigned)v;                 // forward.cu:108 `(unsigned int)node_value`
-        uint32_t outbits = 0;
-        if (is_out) {                                // kernel.h:105-113: {i16 function, i16 outIndex}
-            const uint32_t bits = __float_as_uint(v);
-            func = (unsigned)(int)(int16_t)(bits & 0xFFFF);
-            const unsigned oi = (unsigned)(int)(int16_t)(bits >> 16);
-            outbits = I_OUT | ((oi < (unsigned)g.O ? oi : I_IDX_MASK) << I_IDXB_SHIFT);
-        }
+        const int t = EVOGP_LDG(typ + i);
+        const float v = EVOGP_LDG(val + i);
+        const int ar = node_arity<false>(t);
+        const unsigned func = f32_to_u32(v);         // forward.cu:108 `(unsigned int)node_value`
+        const uint32_t outbits = 0;
         if (ar == 1) {
             const int u = unary_slot(func);
             const int c = i + 1;
-            const uint32_t ci = SA[c * T + tid];
+            const uint32_t ci = SA[c * stride];
             if (a_cplx(ci)) {
-                SB[c * T + tid] = sb;    // same start, same liveness
-                out[own] = make_uint2((C_UA + u) | outbits, 0);
+                SB[c * stride] = sb;    // same start, same liveness
+                out[own] = mk2((uint32_t)(C_UA + u) | outbits, 0);
             } else {
-                uint32_t hdr = (C_UL + u) | outbits | live_push, cst = 0;
-                leaf_desc(__ldg(typ + c), __ldg(val + c), g.V, false, hdr, cst);
-                out[own] = make_uint2(hdr, cst);
+                uint32_t hdr = (uint32_t)(C_UL + u) | outbits | live_push, cst = 0;
+                leaf_desc(EVOGP_LDG(typ + c), EVOGP_LDG(val + c), V, false, hdr, cst);
+                out[own] = mk2(hdr, cst);
             }
         } else if (ar == 2) {
             const int b = binary_slot(func);
             const int x = i + 1;
-            const uint32_t xi = SA[x * T + tid];
+            const uint32_t xi = SA[x * stride];
             const int y = x + a_sz(xi);
-            const uint32_t yi = SA[y * T + tid];
+            const uint32_t yi = SA[y * stride];
             const int cx = a_cplx(xi), cy = a_cplx(yi);
             if (!cx && !cy) {
-                const int tx = __ldg(typ + x), ty = __ldg(typ + y);
-                const float vx = __ldg(val + x), vy = __ldg(val + y);
+                const int tx = EVOGP_LDG(typ + x), ty = EVOGP_LDG(typ + y);
+                const float vx = EVOGP_LDG(val + x), vy = EVOGP_LDG(val + y);
                 if (a_ni(me) == 2) {
                     uint32_t h0 = C_LOAD | live_push, c0 = 0;
-                    leaf_desc(tx, vx, g.V, false, h0, c0);
-                    out[st] = make_uint2(h0, c0);
-                    uint32_t h1 = (C_AL + b) | outbits, c1 = 0;
-                    leaf_desc(ty, vy, g.V, false, h1, c1);
-                    out[st + 1] = make_uint2(h1, c1);
+                    leaf_desc(tx, vx, V, false, h0, c0);
+                    out[st] = mk2(h0, c0);
+                    uint32_t h1 = (uint32_t)(C_AL + b) | outbits, c1 = 0;
+                    leaf_desc(ty, vy, V, false, h1, c1);
+                    out[st + 1] = mk2(h1, c1);
                 } else {
-                    uint32_t hdr = (C_LL + b) | live_push, cst = 0;
-                    leaf_desc(tx, vx, g.V, false, hdr, cst);
-                    leaf_desc(ty, vy, g.V, true, hdr, cst);
-                    out[own] = make_uint2(hdr, cst);
+                    uint32_t hdr = (uint32_t)(C_LL + b) | live_push, cst = 0;
+                    leaf_desc(tx, vx, V, false, hdr, cst);
+                    leaf_desc(ty, vy, V, true, hdr, cst);
+                    out[own] = mk2(hdr, cst);
                 }
             } else if (cx && cy) {
                 const bool x_first = a_need(xi) > a_need(yi);   // ties: right child first, as the reference does
                 const int first = x_first ? x : y, second = x_first ? y : x;
                 const int ni_first = x_first ? a_ni(xi) : a_ni(yi);
-                SB[first * T + tid] = sb;
-                SB[second * T + tid] = (uint32_t)(st + ni_first) | (1u << 11);
-                out[own] = make_uint2((x_first ? (C_SA + b) : (C_AS + b)) | outbits, 0);
+                SB[first * stride] = sb;
+                SB[second * stride] = (uint32_t)(st + ni_first) | (1u << 11);
+                out[own] = mk2((uint32_t)(x_first ? (C_SA + b) : (C_AS + b)) | outbits, 0);
             } else {
                 const int cc = cx ? x : y, lf = cx ? y : x;
-                SB[cc * T + tid] = sb;
-                uint32_t hdr = (cx ? (C_AL + b) : (C_LA + b)) | outbits, cst = 0;
-                leaf_desc(__ldg(typ + lf), __ldg(val + lf), g.V, false, hdr, cst);
-                out[own] = make_uint2(hdr, cst);
+                SB[cc * stride] = sb;
+                uint32_t hdr = (uint32_t)(cx ? (C_AL + b) : (C_LA + b)) | outbits, cst = 0;
+                leaf_desc(EVOGP_LDG(typ + lf), EVOGP_LDG(val + lf), V, false, hdr, cst);
+                out[own] = mk2(hdr, cst);
             }
         } else {
             // IF(a, b, c): produce the three values in descending-need order (ties: c, b, a — the
@@ -220,40 +245,157 @@ __global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
             int pos[3];
             uint32_t inf[3];
             pos[0] = i + 1;
-            inf[0] = SA[pos[0] * T + tid];
+            inf[0] = SA[pos[0] * stride];
             pos[1] = pos[0] + a_sz(inf[0]);
-            inf[1] = SA[pos[1] * T + tid];
+            inf[1] = SA[pos[1] * stride];
             pos[2] = pos[1] + a_sz(inf[1]);
-            inf[2] = SA[pos[2] * T + tid];
+            inf[2] = SA[pos[2] * stride];
             int nd[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) nd[k] = a_cplx(inf[k]) ? a_need(inf[k]) : 0;
-            int ord[3] = {2, 1, 0};   // c, b, a
-            // stable insertion sort by need, descending
-            if (nd[ord[1]] > nd[ord[0]]) { int s = ord[0]; ord[0] = ord[1]; ord[1] = s; }
-            if (nd[ord[2]] > nd[ord[1]]) { int s = ord[1]; ord[1] = ord[2]; ord[2] = s; }
-            if (nd[ord[1]] > nd[ord[0]]) { int s = ord[0]; ord[0] = ord[1]; ord[1] = s; }
+            int o0 = 2, o1 = 1, o2 = 0;   // c, b, a; stable bubble sort by need, descending
+            if (nd[o1] > nd[o0]) { const int s = o0; o0 = o1; o1 = s; }
+            if (nd[o2] > nd[o1]) { const int s = o1; o1 = o2; o2 = s; }
+            if (nd[o1] > nd[o0]) { const int s = o0; o0 = o1; o1 = s; }
             int cur = st;
-            uint32_t src[3] = {0, 0, 0};   // where IF finds a, b, c: 0 acc, 1 stack top, 2 stack top-1
+            uint32_t perm = 0;   // 2 bits per operand a,b,c: 0 acc, 1 stack top, 2 stack top-1
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int k = ord[j];
+                const int k = j == 0 ? o0 : (j == 1 ? o1 : o2);
                 const uint32_t lv = j == 0 ? ((sb >> 11) & 1) : 1u;
-                if (a_cplx(inf[k])) {
-                    SB[pos[k] * T + tid] = (uint32_t)cur | (lv << 11);
-                    cur += a_ni(inf[k]);
+                const uint32_t ik = k == 0 ? inf[0] : (k == 1 ? inf[1] : inf[2]);
+                const int pk = k == 0 ? pos[0] : (k == 1 ? pos[1] : pos[2]);
+                if (a_cplx(ik)) {
+                    SB[pk * stride] = (uint32_t)cur | (lv << 11);
+                    cur += a_ni(ik);
                 } else {
                     uint32_t hdr = C_LOAD | (lv ? I_PUSH : 0), cst = 0;
-                    leaf_desc(__ldg(typ + pos[k]), __ldg(val + pos[k]), g.V, false, hdr, cst);
-                    out[cur] = make_uint2(hdr, cst);
+                    leaf_desc(EVOGP_LDG(typ + pk), EVOGP_LDG(val + pk), V, false, hdr, cst);
+                    out[cur] = mk2(hdr, cst);
                     cur += 1;
                 }
-                src[k] = 2 - j;
+                perm |= (uint32_t)(2 - j) << (2 * k);
             }
-            const uint32_t perm = src[0] | (src[1] << 2) | (src[2] << 4);
-            out[own] = make_uint2(C_IF | outbits | (perm << I_IDXA_SHIFT), 0);
+            out[own] = mk2((uint32_t)C_IF | outbits | (perm << I_IDXA_SHIFT), 0);
         }
     }
+    return root_need;
 }
+
+
+// Multi-output rows (out_len > 1).  The reference's multiOutput branch makes EVERY function
+// node hand its right-most child's value to its father (forward.cu:236-242: `top_val =
+// right_node` is unconditional), so a subtree's value is simply its right-most leaf — the last
+// node of its prefix span — and the only arithmetic with an effect is each OUT node applying its
+// function to those leaves and adding the result to outs[outIndex].  The program is therefore a
+// flat list of leaf-operand instructions, one per OUT node, emitted in the reference's
+// processing order (last node first) so the float sums into outs[] associate identically.
+// No operand stack.  Returns 0, or -1 for a malformed row.
+__host__ __device__ inline int lower_tree_multi(const float *val, const int16_t *typ, int len, int L, int Lp, int V,
+                                                int O, uint2 *out, uint32_t *SA, int stride) {
+    bool bad = len < 1 || len > L;
+    if (bad) len = 0;
+    int slot = 0;
+    for (int i = len - 1; i >= 0 && !bad; --i) {
+        const int t = EVOGP_LDG(typ + i);
+        const int ar = node_arity<true>(t);
+        if (ar == 0) {
+            SA[i * stride] = 1;
+            continue;
+        }
+        int c = i + 1, sz = 1, last[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < ar && !bad) {
+                if (c >= len) {
+                    bad = true;
+                } else {
+                    const int cs = (int)SA[c * stride];
+                    c += cs;
+                    sz += cs;
+                    last[k] = c - 1;   // right-most leaf of child k
+                }
+            }
+        }
+        if (bad) break;
+        SA[i * stride] = (uint32_t)sz;
+        if (!(t & NT_OUT)) continue;
+        const uint32_t bits = f32_bits(EVOGP_LDG(val + i));           // kernel.h:105-113
+        const unsigned func = (unsigned)(int)(int16_t)(bits & 0xFFFF);
+        const unsigned oi = (unsigned)(int)(int16_t)(bits >> 16);
+        const uint32_t outbits = I_OUT | ((oi < (unsigned)O ? oi : I_IDX_MASK) << I_IDXB_SHIFT);
+        if (slot + 2 > Lp) { bad = true; break; }                     // cannot happen: slots <= nodes
+        if (ar == 1) {
+            uint32_t hdr = (uint32_t)(C_UL + unary_slot(func)) | outbits, cst = 0;
+            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, hdr, cst);
+            out[slot++] = mk2(hdr, cst);
+        } else if (ar == 2) {
+            uint32_t h0 = C_LOAD, c0 = 0;
+            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, h0, c0);
+            out[slot++] = mk2(h0, c0);
+            uint32_t h1 = (uint32_t)(C_AL + binary_slot(func)) | outbits, c1 = 0;
+            leaf_desc(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V, false, h1, c1);
+            out[slot++] = mk2(h1, c1);
+        } else {
+            // C_IF3, two slots: {hdr, a} {b, c}; b/c words hold constant bits or a variable index
+            uint32_t hdr = (uint32_t)C_IF3 | outbits, ca = 0, w[2] = {0, 0};
+            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, hdr, ca);
+#pragma unroll
+            for (int k = 1; k < 3; ++k) {
+                uint32_t h = 0, cc = 0;
+                leaf_desc(EVOGP_LDG(typ + last[k]), EVOGP_LDG(val + last[k]), V, false, h, cc);
+                if (h & I_ACONST) {
+                    hdr |= k == 1 ? I_IF3_BCONST : I_IF3_CCONST;
+                    w[k - 1] = cc;
+                } else {
+                    w[k - 1] = (h >> I_IDXA_SHIFT) & I_IDX_MASK;
+                }
+            }
+            out[slot++] = mk2(hdr, ca);
+            out[slot++] = mk2(w[0], w[1]);
+        }
+    }
+    if (!bad && len > 0 && (int)SA[0] != len) bad = true;
+    if (bad || len == 0) {
+        out[0] = mk2(C_NAN, 0);
+        if (Lp > 1) out[1] = mk2(C_END, 0);
+        return -1;
+    }
+    if (slot < Lp) out[slot] = mk2(C_END, 0);
+    return 0;
+}
+
+template <bool MULTI>
+__host__ __device__ inline int lower_tree(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
+                                          int depth_budget, uint2 *out, uint32_t *SA, uint32_t *SB, int stride) {
+    if (MULTI) return lower_tree_multi(val, typ, len, L, Lp, V, O, out, SA, stride);
+    return lower_tree_single(val, typ, len, L, Lp, V, O, depth_budget, out, SA, SB, stride);
+}
+
+#ifdef __CUDACC__
+struct LowerArgs {
+    const float *value;
+    const int16_t *type;
+    const int16_t *size;
+    uint2 *prog;        // [P][Lp]
+    unsigned *sched;    // scheduler words (zeroed by the host before launch)
+    unsigned *flags;    // [0]: count of malformed rows, [1]: max stack need seen
+    int P, L, Lp, V, O, depth_budget;
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
+    extern __shared__ uint32_t scratch[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int n = blockIdx.x * T + tid;
+    if (n >= g.P) return;
+    const int len = g.size[(size_t)n * g.L];
+    const int need = lower_tree<MULTI>(g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, len, g.L, g.Lp, g.V, g.O,
+                                       g.depth_budget, g.prog + (size_t)n * g.Lp, scratch + tid,
+                                       scratch + (size_t)g.L * T + tid, T);
+    if (need < 0) atomicAdd(g.flags, 1u);
+    else if (need > 0) atomicMax(g.flags + 1, (unsigned)need);
+}
+#endif
 
 }  // namespace evogp

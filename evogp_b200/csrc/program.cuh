@@ -25,14 +25,15 @@ namespace evogp {
 //          [8]     PUSH    spill acc to the operand stack before executing
 //          [9]     A_CONST leaf operand A is the constant in .y (else variable idxA)
 //          [10]    B_CONST leaf operand B is the constant in .y (else variable idxB)
-//          [11]    OUT     multi-output node: add result to outs[idxB], forward
-//                          the right-most child's value instead (forward.cu:236-242)
+//          [11]    OUT     multi-output programs only: add the result to outs[idxB]
+//                          (idxB == 0x3FF: index out of range, result dropped)
 //          [21:12] idxA    variable index of leaf A  (C_IF: operand permutation)
 //          [31:22] idxB    variable index of leaf B / output index when OUT
 // At most one operand of an instruction is a constant; the lowering pass inserts
 // a C_LOAD when a node has two constant leaves.
 // ---------------------------------------------------------------------------
 constexpr uint32_t I_PUSH = 1u << 8, I_ACONST = 1u << 9, I_BCONST = 1u << 10, I_OUT = 1u << 11;
+constexpr uint32_t I_IF3_BCONST = 1u << 8, I_IF3_CCONST = 1u << 10;   // C_IF3 reuses the PUSH / B_CONST bits
 constexpr int I_IDXA_SHIFT = 12, I_IDXB_SHIFT = 22;
 constexpr uint32_t I_IDX_MASK = 0x3FFu;
 
@@ -45,6 +46,7 @@ enum : int {
     C_LOAD = 1,  // acc = leafA
     C_IF = 2,    // acc = a > 0 ? b : c; operands are acc / stack top / stack top-1 per idxA
     C_NAN = 3,   // malformed row: acc = NaN
+    C_IF3 = 4,   // multi-output only, 2 slots {hdr, a}{b, c}: r = a > 0 ? b : c on three leaf operands
     C_UA = 8,                // acc = u(acc)
     C_UL = C_UA + NUM_U,     // acc = u(leafA)
     C_AL = C_UL + NUM_U,     // acc = b(acc, leafA)
@@ -58,18 +60,23 @@ enum : int {
 __host__ __device__ inline int unary_slot(unsigned f) { return (f >= (unsigned)F_SIN && f < (unsigned)F_END) ? (int)f - F_SIN : U_ZERO; }
 __host__ __device__ inline int binary_slot(unsigned f) { return (f >= (unsigned)F_ADD && f <= (unsigned)F_GE) ? (int)f - F_ADD : B_ZERO; }
 
-// Upper bound of the operand-stack depth any well-formed row of `len` nodes can need
-// after Sethi-Ullman ordering.  M(d) = fewest nodes of a subtree needing >= d slots:
-// a ternary of three leaves already needs 2 (4 nodes); beyond that the cheapest way
-// to need d is a binary node over two subtrees needing d-1: M(d) = 1 + 2 M(d-1).
+// Upper bound of the operand-stack depth any well-formed row of `len` nodes can need under
+// the lowering pass's ordering (lower.cuh).  need() there is: unary = child; binary with two
+// non-leaf children = max(max, min + 1); ternary = max(n0, n1 + 1, n2 + 2) over its three
+// children sorted by need (a leaf child counts as need 0, so any ternary needs >= 2).
+// M(d) = fewest nodes of a subtree needing >= d:  M(1) = M(2) = 4 (ternary of leaves),
+// M(d) = min(1 + 2 M(d-1), 1 + 3 M(d-2)):  4, 4, 9, 13, 27, 40, 81, 121, 243, 364, 729, 1093.
 __host__ __device__ inline int stack_depth_bound(int len) {
-    int d = 2, m = 4;
     if (len < 4) return 1;
-    while (1 + 2 * m <= len) {
-        m = 1 + 2 * m;
-        d++;
+    int d = 2, m_prev = 4, m_cur = 4;   // M(d-1), M(d)
+    for (;;) {
+        const int a = 1 + 2 * m_cur, b = 1 + 3 * m_prev;
+        const int m_next = a < b ? a : b;
+        if (m_next > len) return d;
+        m_prev = m_cur;
+        m_cur = m_next;
+        ++d;
     }
-    return d;
 }
 
 // ---------------------------------------------------------------------------
@@ -88,7 +95,7 @@ __device__ __forceinline__ float unary_op(float a) {
     else if constexpr (U == F_LOG - F_SIN) return logf(a);
     else if constexpr (U == F_LOOSE_LOG - F_SIN) return a == 0.0f ? -kMaxVal : logf(fabsf(a));
     else if constexpr (U == F_EXP - F_SIN) return expf(a);
-    else if constexpr (U == F_INV - F_SIN) return a == 0.0f ? __int_as_float(0x7fffffff) : 1.0f / a;
+    else if constexpr (U == F_INV - F_SIN) return a == 0.0f ? __int_as_float(0x7fc00000) : 1.0f / a;
     else if constexpr (U == F_LOOSE_INV - F_SIN) {
         if (fabsf(a) <= kDelta) a = copysignf(kDelta, a);
         return 1.0f / a;
@@ -106,7 +113,7 @@ __device__ __forceinline__ float binary_op(float a, float b) {
     if constexpr (B == F_ADD - F_ADD) return __fadd_rn(a, b);   // _rn: never contracted with a neighbour
     else if constexpr (B == F_SUB - F_ADD) return __fsub_rn(a, b);
     else if constexpr (B == F_MUL - F_ADD) return __fmul_rn(a, b);
-    else if constexpr (B == F_DIV - F_ADD) return b == 0.0f ? __int_as_float(0x7fffffff) : a / b;
+    else if constexpr (B == F_DIV - F_ADD) return b == 0.0f ? __int_as_float(0x7fc00000) : a / b;
     else if constexpr (B == F_LOOSE_DIV - F_ADD) {
         if (fabsf(b) <= kDelta) b = copysignf(kDelta, b);
         return a / b;

@@ -76,6 +76,12 @@ int evogp_crossover(int pop_size_ori, int pop_size_new, int gpLen, const float *
  * population of popSize rows of width maxGPLen (compiled programs + scheduler words). */
 size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen);
 
+/* Measurement hook: when both are non-NULL cudaEvent_t handles, every evaluation entry point
+ * records `begin_event` immediately before and `end_event` immediately after the replay kernel
+ * launch on the caller's stream (so the tree-evaluation kernel can be timed apart from the
+ * lowering pass).  Pass NULLs to switch it off. */
+void evogp_eval_set_timing_events(void *begin_event, void *end_event);
+
 /* replaces evaluate(), kernel.h:71-81 (forward.cu:353-371): tree n on variables[n, :] -> results[n, :outLen]. */
 int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
                    const int16_t *type, const int16_t *subtree_size, const float *variables, float *results,

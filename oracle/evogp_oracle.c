@@ -573,3 +573,7 @@ int oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* scalar operator hooks for tests/host_lower_harness.cu (replays lowered programs on the CPU) */
+float oracle_apply_unary(unsigned f, float a) { return op_unary(f, a); }
+float oracle_apply_binary(unsigned f, float a, float b) { return op_binary(f, a, b); }
