@@ -18,6 +18,7 @@
 //        atomics on fitness, no averaging kernel.
 #include <cooperative_groups.h>
 #include "lower.cuh"
+#include "fastpath_k8.inc"
 
 namespace evogp {
 
@@ -170,10 +171,8 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
             if constexpr (ROWWISE) xl = g.X + (size_t)tree * g.V;
             else xl = Xs + pass_off + lane_off;
 
-            auto fetch = [&](float(&l)[K], bool is_const, float cst, uint32_t idx) {
-                if (is_const) {
-                    FOR_K l[k] = cst;
-                } else if constexpr (ROWWISE) {
+            auto fetch_var = [&](float(&l)[K], uint32_t idx) {
+                if constexpr (ROWWISE) {
                     const float x = __ldg(xl + idx);
                     FOR_K l[k] = x;
                 } else {
@@ -184,132 +183,130 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
             float acc[K];
             FOR_K acc[k] = 0.0f;
             if constexpr (MULTI) {
-                for (int o = 0; o < g.O; ++o) {
-                    float z[K];
-                    FOR_K z[k] = 0.0f;
-                    st_vec<K>(outs + o * SLOT + lane_off, z);
-                }
+                for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
             }
             int sp = 0, pc = 0;
-            uint2 ins = prog[0];
-            while (true) {
+
+            // ---- generic interpreter: one instruction per call; two stages (operands by form,
+            //      then ONE switch over the operator) keep it small enough to stay cache-resident ----
+            auto step = [&]() -> bool {
+                const uint2 ins = prog[pc];
                 const uint32_t w = ins.x;
                 const float cst = __uint_as_float(ins.y);
-                ++pc;
-                ins = prog[pc < g.Lp ? pc : g.Lp - 1];   // prefetch the next slot
-                if constexpr (!MULTI) {   // multi-output programs have no operand stack
-                    if (w & I_PUSH) {
-                        st_vec<K>(stack + sp * SLOT + lane_off, acc);
-                        ++sp;
-                    }
-                }
+                const uint32_t code = w & 0xFFu, form = code >> 4, op = code & 15u;
                 const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
-
-// result r of a function node.  Multi-output programs (lower_tree_multi) consist of OUT
-// instructions only: the result is added to outs[idxB]; nothing consumes acc afterwards
-// except the C_LOAD -> C_AL pair of a binary node.
-#define FINISH(r)                                                                 \
-    if constexpr (MULTI) {                                                        \
-        if ((w & I_OUT) && ib != I_IDX_MASK) {                                    \
-            float o_[K];                                                          \
-            ld_vec<K>(o_, outs + ib * SLOT + lane_off);                           \
-            FOR_K o_[k] += r[k];                                                  \
-            st_vec<K>(outs + ib * SLOT + lane_off, o_);                           \
-        }                                                                         \
-    }                                                                             \
-    FOR_K acc[k] = r[k];
-
-#define CASE_U(u)                                                                 \
-    case C_UA + u: {                                                              \
-        float r[K];                                                               \
-        FOR_K r[k] = unary_op<u>(acc[k]);                                         \
-        FINISH(r)                                                            \
-    } break;                                                                      \
-    case C_UL + u: {                                                              \
-        float l[K], r[K];                                                         \
-        fetch(l, w & I_ACONST, cst, ia);                                          \
-        FOR_K r[k] = unary_op<u>(l[k]);                                           \
-        FINISH(r)                                                              \
-    } break;
-
-#define CASE_B(b)                                                                 \
-    case C_AL + b: {                                                              \
-        float l[K], r[K];                                                         \
-        fetch(l, w & I_ACONST, cst, ia);                                          \
-        FOR_K r[k] = binary_op<b>(acc[k], l[k]);                                  \
-        FINISH(r)                                                              \
-    } break;                                                                      \
-    case C_LA + b: {                                                              \
-        float l[K], r[K];                                                         \
-        fetch(l, w & I_ACONST, cst, ia);                                          \
-        FOR_K r[k] = binary_op<b>(l[k], acc[k]);                                  \
-        FINISH(r)                                                            \
-    } break;                                                                      \
-    case C_LL + b: {                                                              \
-        float l[K], m[K];                                                         \
-        fetch(l, w & I_ACONST, cst, ia);                                          \
-        fetch(m, w & I_BCONST, cst, ib);                                          \
-        FOR_K acc[k] = binary_op<b>(l[k], m[k]);                                  \
-    } break;                                                                      \
-    case C_SA + b: {                                                              \
-        float s[K], r[K];                                                         \
-        --sp;                                                                     \
-        ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
-        FOR_K r[k] = binary_op<b>(s[k], acc[k]);                                  \
-        FINISH(r)                                                            \
-    } break;                                                                      \
-    case C_AS + b: {                                                              \
-        float s[K], r[K];                                                         \
-        --sp;                                                                     \
-        ld_vec<K>(s, stack + sp * SLOT + lane_off);                               \
-        FOR_K r[k] = binary_op<b>(acc[k], s[k]);                                  \
-        FINISH(r)                                                              \
-    } break;
-
-                switch (w & 0xFFu) {
-                case C_END: goto tree_done;
-                case C_LOAD: fetch(acc, w & I_ACONST, cst, ia); break;
-                case C_NAN: {
-                    FOR_K acc[k] = __int_as_float(0x7fc00000);
-                    if constexpr (MULTI)
-                        for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
-                } break;
-                case C_IF3: {
+                ++pc;
+                if (code == C_END) return true;
+                float x[K], y[K], r[K];
+                if (code == C_IF3) {
                     if constexpr (MULTI) {   // {hdr, a}{b, c}: three leaf operands
-                        float a[K], b[K], c[K], r[K];
-                        const uint2 ext = ins;           // second slot (already prefetched)
+                        const uint2 ext = prog[pc];
                         ++pc;
-                        ins = prog[pc < g.Lp ? pc : g.Lp - 1];
-                        fetch(a, w & I_ACONST, cst, ia);
-                        fetch(b, w & I_IF3_BCONST, __uint_as_float(ext.x), ext.x & I_IDX_MASK);
-                        fetch(c, w & I_IF3_CCONST, __uint_as_float(ext.y), ext.y & I_IDX_MASK);
-                        FOR_K r[k] = a[k] > 0.0f ? b[k] : c[k];
-                        FINISH(r)
+                        float z[K];
+                        if (w & I_IF3_ACONST) { FOR_K x[k] = cst; } else fetch_var(x, ia);
+                        if (w & I_IF3_BCONST) { FOR_K y[k] = __uint_as_float(ext.x); } else fetch_var(y, ext.x & I_IDX_MASK);
+                        if (w & I_IF3_CCONST) { FOR_K z[k] = __uint_as_float(ext.y); } else fetch_var(z, ext.y & I_IDX_MASK);
+                        FOR_K r[k] = x[k] > 0.0f ? y[k] : z[k];
+                    } else {
+                        FOR_K r[k] = 0.0f;
                     }
-                } break;
-                case C_IF: {
-                    float t1[K], t2[K], a[K], b[K], c[K], r[K];
-                    sp -= 2;
-                    ld_vec<K>(t1, stack + (sp + 1) * SLOT + lane_off);
-                    ld_vec<K>(t2, stack + sp * SLOT + lane_off);
-                    const uint32_t sa = ia & 3, sb = (ia >> 2) & 3, sc = (ia >> 4) & 3;
-                    FOR_K {
-                        a[k] = sa == 0 ? acc[k] : (sa == 1 ? t1[k] : t2[k]);
-                        b[k] = sb == 0 ? acc[k] : (sb == 1 ? t1[k] : t2[k]);
-                        c[k] = sc == 0 ? acc[k] : (sc == 1 ? t1[k] : t2[k]);
-                        r[k] = a[k] > 0.0f ? b[k] : c[k];   // forward.cu:223
+                } else {
+                    if constexpr (!MULTI) {   // multi-output programs have no operand stack
+                        if (w & I_PUSH) {
+                            st_vec<K>(stack + sp * SLOT + lane_off, acc);
+                            ++sp;
+                        }
                     }
-                    FINISH(r)
-                } break;
-                    CASE_U(0) CASE_U(1) CASE_U(2) CASE_U(3) CASE_U(4) CASE_U(5) CASE_U(6) CASE_U(7)
-                    CASE_U(8) CASE_U(9) CASE_U(10) CASE_U(11) CASE_U(12) CASE_U(13) CASE_U(14) CASE_U(15)
-                    CASE_B(0) CASE_B(1) CASE_B(2) CASE_B(3) CASE_B(4) CASE_B(5) CASE_B(6)
-                    CASE_B(7) CASE_B(8) CASE_B(9) CASE_B(10) CASE_B(11) CASE_B(12) CASE_B(13)
-                default: break;
+                    switch (form) {
+                    case FM_MISC:
+                        if (code == C_LOAD_V) { fetch_var(acc, ia); return false; }
+                        if (code == C_LOAD_K) { FOR_K acc[k] = cst; return false; }
+                        if (code == C_IF) {   // forward.cu:223
+                            float t1[K], t2[K];
+                            sp -= 2;
+                            ld_vec<K>(t1, stack + (sp + 1) * SLOT + lane_off);
+                            ld_vec<K>(t2, stack + sp * SLOT + lane_off);
+                            const uint32_t sa = ia & 3, sb = (ia >> 2) & 3, sc = (ia >> 4) & 3;
+                            FOR_K {
+                                const float a = sa == 0 ? acc[k] : (sa == 1 ? t1[k] : t2[k]);
+                                const float b = sb == 0 ? acc[k] : (sb == 1 ? t1[k] : t2[k]);
+                                const float c = sc == 0 ? acc[k] : (sc == 1 ? t1[k] : t2[k]);
+                                acc[k] = a > 0.0f ? b : c;
+                            }
+                            return false;
+                        }
+                        // C_NAN (malformed row) and anything unknown
+                        FOR_K acc[k] = __int_as_float(0x7fc00000);
+                        if constexpr (MULTI)
+                            for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
+                        return false;
+                    case FM_UA: FOR_K x[k] = acc[k]; break;
+                    case FM_UV: fetch_var(x, ia); break;
+                    case FM_UK: FOR_K x[k] = cst; break;
+                    case FM_AV: FOR_K x[k] = acc[k]; fetch_var(y, ia); break;
+                    case FM_AK: FOR_K { x[k] = acc[k]; y[k] = cst; } break;
+                    case FM_VA: fetch_var(x, ia); FOR_K y[k] = acc[k]; break;
+                    case FM_KA: FOR_K { x[k] = cst; y[k] = acc[k]; } break;
+                    case FM_VV: fetch_var(x, ia); fetch_var(y, ib); break;
+                    case FM_VK: fetch_var(x, ia); FOR_K y[k] = cst; break;
+                    case FM_KV: FOR_K x[k] = cst; fetch_var(y, ia); break;
+                    case FM_SA: --sp; ld_vec<K>(x, stack + sp * SLOT + lane_off); FOR_K y[k] = acc[k]; break;
+                    case FM_AS: --sp; FOR_K x[k] = acc[k]; ld_vec<K>(y, stack + sp * SLOT + lane_off); break;
+                    default: FOR_K { x[k] = 0.0f; y[k] = 0.0f; } break;
+                    }
+                    if (form <= FM_UK) {
+#define U_CASE(u) case u: FOR_K r[k] = unary_op<u>(x[k]); break;
+                        switch (op) {
+                            U_CASE(0) U_CASE(1) U_CASE(2) U_CASE(3) U_CASE(4) U_CASE(5) U_CASE(6) U_CASE(7)
+                            U_CASE(8) U_CASE(9) U_CASE(10) U_CASE(11) U_CASE(12) U_CASE(13) U_CASE(14)
+                        default: FOR_K r[k] = 0.0f; break;
+                        }
+#undef U_CASE
+                    } else {
+#define B_CASE(b) case b: FOR_K r[k] = binary_op<b>(x[k], y[k]); break;
+                        switch (op) {
+                            B_CASE(0) B_CASE(1) B_CASE(2) B_CASE(3) B_CASE(4) B_CASE(5) B_CASE(6)
+                            B_CASE(7) B_CASE(8) B_CASE(9) B_CASE(10) B_CASE(11) B_CASE(12)
+                        default: FOR_K r[k] = 0.0f; break;
+                        }
+#undef B_CASE
+                    }
                 }
-                if (pc >= g.Lp) break;
+                if constexpr (MULTI) {   // every instruction of a multi-output program is an OUT node (or its LOAD)
+                    if ((w & I_OUT) && ib != I_IDX_MASK) {
+                        float o_[K];
+                        ld_vec<K>(o_, outs + ib * SLOT + lane_off);
+                        FOR_K o_[k] += r[k];
+                        st_vec<K>(outs + ib * SLOT + lane_off, o_);
+                    }
+                }
+                FOR_K acc[k] = r[k];
+                return false;
+            };
+
+            if constexpr (K == 8 && !MULTI && !ROWWISE) {
+                // PTX fast path (fastpath_k8.inc): brx.idx jump table, operands by opcode
+                const uint32_t prog_base = smem_u32(prog), stack_base = smem_u32(stack + lane_off);
+                uint32_t pc_addr = prog_base, sp_addr = stack_base, status;
+                const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
+                for (;;) {
+                    asm volatile(EVOGP_FASTPATH_K8_ASM
+                                 : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                   "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "+r"(sp_addr), "=r"(status)
+                                 : "r"(xl_addr), "r"(npb)
+                                 : "memory");
+                    if (status == 0) break;
+                    pc = (int)((pc_addr - prog_base) >> 3);
+                    sp = (int)((sp_addr - stack_base) / (SLOT * 4));
+                    if (step()) break;
+                    pc_addr = prog_base + ((uint32_t)pc << 3);
+                    sp_addr = stack_base + (uint32_t)sp * (SLOT * 4);
+                }
+            } else {
+                while (!step()) {
+                }
             }
-        tree_done:
+
             // ---- per-pass epilogue ----
             if (g.mode <= MODE_ABS) {
                 if constexpr (MULTI) {
@@ -383,7 +380,9 @@ static int device_props() {
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static inline int prog_pitch(unsigned L) { return (int)((L + 1) & ~1u); }
+// row pitch in slots: one spare slot so that every program ends in C_END (the fast path never
+// checks a bound) and stays a multiple of 16 bytes for the bulk copy
+static inline int prog_pitch(unsigned L) { return (int)((L + 2) & ~1u); }
 
 struct Workspace {
     uint2 *prog;
@@ -405,7 +404,7 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
                         const int16_t *type, const int16_t *size, int depth, cudaStream_t st) {
     // threads per CTA limited by the [2][L][T] u32 scratch
     int T = 128;
-    while (T > 32 && (size_t)2 * L * T * 4 > 160 * 1024) T -= 32;
+    while (T > 8 && (size_t)2 * L * T * 4 > 160 * 1024) T >>= 1;   // L = 1024 -> 16 threads (128 KB)
     const size_t smem = (size_t)2 * L * T * 4;
     static bool attr_done[2] = {false, false};
     if (!attr_done[MULTI]) {

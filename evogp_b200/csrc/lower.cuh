@@ -67,16 +67,35 @@ __host__ __device__ __forceinline__ int node_arity(int t) {
     return (t == NT_VAR || t == NT_CONST) ? 0 : (t == NT_UFUNC ? 1 : (t == NT_BFUNC ? 2 : 3));
 }
 
-// leaf operand descriptor for slot A (shift 12 / flag A_CONST) or B (shift 22 / B_CONST)
-__host__ __device__ __forceinline__ void leaf_desc(int t, float v, int V, bool slotB, uint32_t &hdr, uint32_t &cst) {
+// a leaf operand: constant (bits) or variable (clamped index)
+struct Leaf {
+    bool is_const;
+    uint32_t bits;   // constant bits, or variable index
+};
+__host__ __device__ __forceinline__ Leaf leaf_of(int t, float v, int V) {
+    Leaf l;
     if ((t & NT_MASK) == NT_CONST) {
-        hdr |= slotB ? I_BCONST : I_ACONST;
-        cst = f32_bits(v);
+        l.is_const = true;
+        l.bits = f32_bits(v);
     } else {
         int idx = f32_to_i32(v);               // forward.cu:100 `(int)node_value`
         idx = idx < 0 ? 0 : (idx >= V ? V - 1 : idx);   // reference reads out of bounds here; clamp
-        hdr |= (uint32_t)idx << (slotB ? I_IDXB_SHIFT : I_IDXA_SHIFT);
+        l.is_const = false;
+        l.bits = (uint32_t)idx;
     }
+    return l;
+}
+// single-leaf instruction of form `fv` (variable) / `fk` (constant): LOAD, unary, AV/AK, VA/KA
+__host__ __device__ __forceinline__ uint2 leaf_instr(int fv_code, int fk_code, Leaf l, uint32_t flags) {
+    uint2 r;
+    if (l.is_const) {
+        r.x = (uint32_t)fk_code | flags;
+        r.y = l.bits;
+    } else {
+        r.x = (uint32_t)fv_code | flags | (l.bits << I_IDXA_SHIFT);
+        r.y = 0;
+    }
+    return r;
 }
 
 __host__ __device__ __forceinline__ uint2 mk2(uint32_t a, uint32_t b) {
@@ -169,9 +188,7 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
     {
         const uint32_t r = SA[0];
         if (!a_cplx(r)) {   // the tree is a single leaf
-            uint32_t hdr = C_LOAD, cst = 0;
-            leaf_desc(EVOGP_LDG(typ), EVOGP_LDG(val), V, false, hdr, cst);
-            out[0] = mk2(hdr, cst);
+            out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ), EVOGP_LDG(val), V), 0);
             if (Lp > 1) out[1] = mk2(C_END, 0);
             return 0;
         }
@@ -189,18 +206,16 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
         const float v = EVOGP_LDG(val + i);
         const int ar = node_arity<false>(t);
         const unsigned func = f32_to_u32(v);         // forward.cu:108 `(unsigned int)node_value`
-        const uint32_t outbits = 0;
         if (ar == 1) {
             const int u = unary_slot(func);
             const int c = i + 1;
             const uint32_t ci = SA[c * stride];
             if (a_cplx(ci)) {
                 SB[c * stride] = sb;    // same start, same liveness
-                out[own] = mk2((uint32_t)(C_UA + u) | outbits, 0);
+                out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
             } else {
-                uint32_t hdr = (uint32_t)(C_UL + u) | outbits | live_push, cst = 0;
-                leaf_desc(EVOGP_LDG(typ + c), EVOGP_LDG(val + c), V, false, hdr, cst);
-                out[own] = mk2(hdr, cst);
+                out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u),
+                                      leaf_of(EVOGP_LDG(typ + c), EVOGP_LDG(val + c), V), live_push);
             }
         } else if (ar == 2) {
             const int b = binary_slot(func);
@@ -212,18 +227,16 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
             if (!cx && !cy) {
                 const int tx = EVOGP_LDG(typ + x), ty = EVOGP_LDG(typ + y);
                 const float vx = EVOGP_LDG(val + x), vy = EVOGP_LDG(val + y);
-                if (a_ni(me) == 2) {
-                    uint32_t h0 = C_LOAD | live_push, c0 = 0;
-                    leaf_desc(tx, vx, V, false, h0, c0);
-                    out[st] = mk2(h0, c0);
-                    uint32_t h1 = (uint32_t)(C_AL + b) | outbits, c1 = 0;
-                    leaf_desc(ty, vy, V, false, h1, c1);
-                    out[st + 1] = mk2(h1, c1);
+                const Leaf lx = leaf_of(tx, vx, V), ly = leaf_of(ty, vy, V);
+                if (a_ni(me) == 2) {          // two constants: load the first, then acc (op) const
+                    out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, lx, live_push);
+                    out[st + 1] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), ly, 0);
+                } else if (!lx.is_const && !ly.is_const) {
+                    out[own] = mk2((uint32_t)opcode(FM_VV, b) | live_push | (lx.bits << I_IDXA_SHIFT) | (ly.bits << I_IDXB_SHIFT), 0);
+                } else if (!lx.is_const) {
+                    out[own] = mk2((uint32_t)opcode(FM_VK, b) | live_push | (lx.bits << I_IDXA_SHIFT), ly.bits);
                 } else {
-                    uint32_t hdr = (uint32_t)(C_LL + b) | live_push, cst = 0;
-                    leaf_desc(tx, vx, V, false, hdr, cst);
-                    leaf_desc(ty, vy, V, true, hdr, cst);
-                    out[own] = mk2(hdr, cst);
+                    out[own] = mk2((uint32_t)opcode(FM_KV, b) | live_push | (ly.bits << I_IDXA_SHIFT), lx.bits);
                 }
             } else if (cx && cy) {
                 const bool x_first = a_need(xi) > a_need(yi);   // ties: right child first, as the reference does
@@ -231,13 +244,13 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
                 const int ni_first = x_first ? a_ni(xi) : a_ni(yi);
                 SB[first * stride] = sb;
                 SB[second * stride] = (uint32_t)(st + ni_first) | (1u << 11);
-                out[own] = mk2((uint32_t)(x_first ? (C_SA + b) : (C_AS + b)) | outbits, 0);
+                out[own] = mk2((uint32_t)opcode(x_first ? FM_SA : FM_AS, b), 0);
             } else {
                 const int cc = cx ? x : y, lf = cx ? y : x;
                 SB[cc * stride] = sb;
-                uint32_t hdr = (uint32_t)(cx ? (C_AL + b) : (C_LA + b)) | outbits, cst = 0;
-                leaf_desc(EVOGP_LDG(typ + lf), EVOGP_LDG(val + lf), V, false, hdr, cst);
-                out[own] = mk2(hdr, cst);
+                const Leaf l = leaf_of(EVOGP_LDG(typ + lf), EVOGP_LDG(val + lf), V);
+                out[own] = cx ? leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), l, 0)
+                              : leaf_instr(opcode(FM_VA, b), opcode(FM_KA, b), l, 0);
             }
         } else {
             // IF(a, b, c): produce the three values in descending-need order (ties: c, b, a — the
@@ -269,14 +282,13 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
                     SB[pk * stride] = (uint32_t)cur | (lv << 11);
                     cur += a_ni(ik);
                 } else {
-                    uint32_t hdr = C_LOAD | (lv ? I_PUSH : 0), cst = 0;
-                    leaf_desc(EVOGP_LDG(typ + pk), EVOGP_LDG(val + pk), V, false, hdr, cst);
-                    out[cur] = mk2(hdr, cst);
+                    out[cur] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ + pk), EVOGP_LDG(val + pk), V),
+                                          lv ? I_PUSH : 0);
                     cur += 1;
                 }
                 perm |= (uint32_t)(2 - j) << (2 * k);
             }
-            out[own] = mk2((uint32_t)C_IF | outbits | (perm << I_IDXA_SHIFT), 0);
+            out[own] = mk2((uint32_t)C_IF | (perm << I_IDXA_SHIFT), 0);
         }
     }
     return root_need;
@@ -326,33 +338,23 @@ __host__ __device__ inline int lower_tree_multi(const float *val, const int16_t 
         const uint32_t outbits = I_OUT | ((oi < (unsigned)O ? oi : I_IDX_MASK) << I_IDXB_SHIFT);
         if (slot + 2 > Lp) { bad = true; break; }                     // cannot happen: slots <= nodes
         if (ar == 1) {
-            uint32_t hdr = (uint32_t)(C_UL + unary_slot(func)) | outbits, cst = 0;
-            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, hdr, cst);
-            out[slot++] = mk2(hdr, cst);
+            const int u = unary_slot(func);
+            out[slot++] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u),
+                                     leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V), outbits);
         } else if (ar == 2) {
-            uint32_t h0 = C_LOAD, c0 = 0;
-            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, h0, c0);
-            out[slot++] = mk2(h0, c0);
-            uint32_t h1 = (uint32_t)(C_AL + binary_slot(func)) | outbits, c1 = 0;
-            leaf_desc(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V, false, h1, c1);
-            out[slot++] = mk2(h1, c1);
+            const int b = binary_slot(func);
+            out[slot++] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V), 0);
+            out[slot++] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b),
+                                     leaf_of(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V), outbits);
         } else {
             // C_IF3, two slots: {hdr, a} {b, c}; b/c words hold constant bits or a variable index
-            uint32_t hdr = (uint32_t)C_IF3 | outbits, ca = 0, w[2] = {0, 0};
-            leaf_desc(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V, false, hdr, ca);
-#pragma unroll
-            for (int k = 1; k < 3; ++k) {
-                uint32_t h = 0, cc = 0;
-                leaf_desc(EVOGP_LDG(typ + last[k]), EVOGP_LDG(val + last[k]), V, false, h, cc);
-                if (h & I_ACONST) {
-                    hdr |= k == 1 ? I_IF3_BCONST : I_IF3_CCONST;
-                    w[k - 1] = cc;
-                } else {
-                    w[k - 1] = (h >> I_IDXA_SHIFT) & I_IDX_MASK;
-                }
-            }
-            out[slot++] = mk2(hdr, ca);
-            out[slot++] = mk2(w[0], w[1]);
+            const Leaf la = leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V);
+            const Leaf lb = leaf_of(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V);
+            const Leaf lc = leaf_of(EVOGP_LDG(typ + last[2]), EVOGP_LDG(val + last[2]), V);
+            const uint32_t hdr = (uint32_t)C_IF3 | outbits | (la.is_const ? I_IF3_ACONST : (la.bits << I_IDXA_SHIFT)) |
+                                 (lb.is_const ? I_IF3_BCONST : 0u) | (lc.is_const ? I_IF3_CCONST : 0u);
+            out[slot++] = mk2(hdr, la.is_const ? la.bits : 0u);
+            out[slot++] = mk2(lb.bits, lc.bits);
         }
     }
     if (!bad && len > 0 && (int)SA[0] != len) bad = true;

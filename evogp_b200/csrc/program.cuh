@@ -10,7 +10,7 @@
 // their parent), orders sibling subtrees Sethi-Ullman style so the operand stack
 // never holds more than ~log2(L) live vectors (it lives in shared memory, one
 // float4 column per lane), and turns each function node into ONE instruction whose
-// case label already says where its operands are.
+// opcode already says where its operands are.
 //
 // Values computed per node are exactly the reference's: reordering sibling
 // evaluation does not change any operand of any operator.
@@ -21,19 +21,20 @@ namespace evogp {
 
 // ---------------------------------------------------------------------------
 // instruction word (8 bytes): {header, constant}
-//   header [7:0]   opcode (see below)
-//          [8]     PUSH    spill acc to the operand stack before executing
-//          [9]     A_CONST leaf operand A is the constant in .y (else variable idxA)
-//          [10]    B_CONST leaf operand B is the constant in .y (else variable idxB)
+//   header [7:0]   opcode = form * 16 + op      (form and op tables below)
+//          [8]     PUSH    spill acc to the operand stack before executing; only ever set on
+//                          instructions that start a fresh value (LOAD_*, U?V/U?K, VV, VK, KV)
 //          [11]    OUT     multi-output programs only: add the result to outs[idxB]
-//                          (idxB == 0x3FF: index out of range, result dropped)
-//          [21:12] idxA    variable index of leaf A  (C_IF: operand permutation)
-//          [31:22] idxB    variable index of leaf B / output index when OUT
-// At most one operand of an instruction is a constant; the lowering pass inserts
-// a C_LOAD when a node has two constant leaves.
+//                          (idxB == 0x3FF: output index out of range, result dropped)
+//          [21:12] idxA    variable index of the (first) variable operand; C_IF: operand permutation
+//          [31:22] idxB    variable index of the second variable operand (VV) / output index when OUT
+//   constant       the constant operand of a *K* form, bit-cast
+// Operand kinds are part of the opcode, so the replay loop never tests a flag to find an operand:
+//   A = accumulator, V = variable (dataset column), K = constant, S = pop from the operand stack.
 // ---------------------------------------------------------------------------
-constexpr uint32_t I_PUSH = 1u << 8, I_ACONST = 1u << 9, I_BCONST = 1u << 10, I_OUT = 1u << 11;
-constexpr uint32_t I_IF3_BCONST = 1u << 8, I_IF3_CCONST = 1u << 10;   // C_IF3 reuses the PUSH / B_CONST bits
+constexpr uint32_t I_PUSH = 1u << 8, I_OUT = 1u << 11;
+// C_IF3 (multi-output, three leaf operands) flags which of a, b, c are constants
+constexpr uint32_t I_IF3_BCONST = 1u << 8, I_IF3_ACONST = 1u << 9, I_IF3_CCONST = 1u << 10;
 constexpr int I_IDXA_SHIFT = 12, I_IDXB_SHIFT = 22;
 constexpr uint32_t I_IDX_MASK = 0x3FFu;
 
@@ -41,22 +42,34 @@ constexpr int NUM_U = 16;  // 15 unary functions (ids 14..28) + "unknown id -> 0
 constexpr int NUM_B = 14;  // 13 binary functions (ids 1..13) + "unknown id -> 0"
 constexpr int U_ZERO = 15, B_ZERO = 13;
 
+// forms (opcode >> 4)
 enum : int {
-    C_END = 0,   // stop
-    C_LOAD = 1,  // acc = leafA
-    C_IF = 2,    // acc = a > 0 ? b : c; operands are acc / stack top / stack top-1 per idxA
-    C_NAN = 3,   // malformed row: acc = NaN
-    C_IF3 = 4,   // multi-output only, 2 slots {hdr, a}{b, c}: r = a > 0 ? b : c on three leaf operands
-    C_UA = 8,                // acc = u(acc)
-    C_UL = C_UA + NUM_U,     // acc = u(leafA)
-    C_AL = C_UL + NUM_U,     // acc = b(acc, leafA)
-    C_LA = C_AL + NUM_B,     // acc = b(leafA, acc)
-    C_LL = C_LA + NUM_B,     // acc = b(leafA, leafB)
-    C_SA = C_LL + NUM_B,     // acc = b(pop, acc)
-    C_AS = C_SA + NUM_B,     // acc = b(acc, pop)
-    C_COUNT = C_AS + NUM_B
+    FM_MISC = 0,
+    FM_UA = 1,   // acc = u(acc)
+    FM_UV = 2,   // acc = u(var A)
+    FM_UK = 3,   // acc = u(const)
+    FM_AV = 4,   // acc = b(acc, var A)
+    FM_AK = 5,   // acc = b(acc, const)
+    FM_VA = 6,   // acc = b(var A, acc)
+    FM_KA = 7,   // acc = b(const, acc)
+    FM_VV = 8,   // acc = b(var A, var B)
+    FM_VK = 9,   // acc = b(var A, const)
+    FM_KV = 10,  // acc = b(const, var A)
+    FM_SA = 11,  // acc = b(pop, acc)
+    FM_AS = 12,  // acc = b(acc, pop)
+    FM_COUNT = 13
 };
-
+// FM_MISC opcodes
+enum : int {
+    C_END = 0,     // stop
+    C_LOAD_V = 1,  // acc = var A
+    C_LOAD_K = 2,  // acc = const
+    C_NAN = 3,     // malformed row: result NaN
+    C_IF = 4,      // acc = a > 0 ? b : c; operands are acc / stack top / stack top-1 per idxA
+    C_IF3 = 5,     // multi-output only, 2 slots {hdr, a}{b, c}: r = a > 0 ? b : c on three leaf operands
+    C_COUNT = FM_COUNT * 16
+};
+__host__ __device__ inline int opcode(int form, int op) { return form * 16 + op; }
 __host__ __device__ inline int unary_slot(unsigned f) { return (f >= (unsigned)F_SIN && f < (unsigned)F_END) ? (int)f - F_SIN : U_ZERO; }
 __host__ __device__ inline int binary_slot(unsigned f) { return (f >= (unsigned)F_ADD && f <= (unsigned)F_GE) ? (int)f - F_ADD : B_ZERO; }
 

