@@ -1,0 +1,221 @@
+"""-m gpu: the Python surface (Forest / GenerateDescriptor / GeneticProgramming / problems / pipeline)
+on top of the torch operator boundary, checked against the oracle."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_util as G
+from conftest import make_data
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(native):
+    native.load_ops()
+    import evogp_b200.tree as tree
+    import evogp_b200.algorithm as algorithm
+    import evogp_b200.problem as problem
+    import evogp_b200.pipeline as pipeline
+    return tree, algorithm, problem, pipeline
+
+
+def host(f):
+    return f.batch_node_value.cpu().numpy(), f.batch_node_type.cpu().numpy(), f.batch_subtree_size.cpu().numpy()
+
+
+def test_descriptor_matches_tutorial_tensors(api):
+    tree = api[0]
+    d = tree.GenerateDescriptor(max_tree_len=32, input_len=2, output_len=1, using_funcs=["+", "-", "*", "/"],
+                                max_layer_cnt=5, const_samples=[-1, 0, 1])
+    assert d.roulette_funcs.cpu().tolist()[:6] == [0.0, 0.25, 0.5, 0.75, 1.0, 1.0]
+    assert d.depth2leaf_probs.cpu().tolist() == pytest.approx([0.2] * 4 + [1.0] * 6)
+    d2 = d.update(max_layer_cnt=3)
+    assert d2.depth2leaf_probs.cpu().tolist() == pytest.approx([0.2] * 2 + [1.0] * 8) and d2.max_tree_len == 32
+    with pytest.raises(AssertionError):
+        tree.GenerateDescriptor(max_tree_len=8, input_len=2, output_len=1, using_funcs=["+"], max_layer_cnt=5, const_samples=[0])
+    w = tree.GenerateDescriptor(max_tree_len=64, input_len=2, output_len=1, using_funcs={"sin": 3.0, "+": 1.0}, max_layer_cnt=4,
+                                const_range=(-2, 2), sample_cnt=16)
+    r = w.roulette_funcs.cpu().numpy()
+    assert r[0] == 0 and r[1] == pytest.approx(0.25) and r[14] == pytest.approx(1.0) and w.const_samples.shape == (16,)
+
+
+def test_forest_api_against_oracle(api, orc):
+    tree = api[0]
+    torch.manual_seed(3)
+    d = tree.GenerateDescriptor(max_tree_len=64, input_len=3, output_len=1, using_funcs=["+", "-", "*", "max", "neg"],
+                                max_layer_cnt=5, const_samples=[-1, 0.5, 2])
+    f = tree.Forest.random_generate(3000, d)
+    v, t, s = host(f)
+    orc.check_forest(v, t, s, input_len=3)
+    X, y = make_data(77, 3, seed=2)
+    fit = f.SR_fitness(torch.from_numpy(X), torch.from_numpy(y))
+    G.assert_close_fitness(fit, orc.sr_fitness(v, t, s, X, y), rtol=1e-5, what="Forest.SR_fitness")
+    for mode in ("hybrid parallel", "data parallel", "tree parallel", "auto"):
+        assert G.same_bits(f.SR_fitness(X.tolist(), y.tolist(), execute_mode=mode), fit)
+    with pytest.raises(AssertionError):
+        f.SR_fitness(X, y, execute_mode="bogus")
+    bf = f.batch_forward(torch.from_numpy(X).cuda())
+    assert bf.shape == (3000, 77, 1) and G.same_bits(bf, orc.batch_forward(v, t, s, X, 1))
+    Xrow = np.random.default_rng(1).uniform(-1, 1, (3000, 3)).astype(np.float32)
+    assert G.same_bits(f.forward(torch.from_numpy(Xrow)), orc.evaluate(v, t, s, Xrow, 1))
+    # container protocol
+    sub = f[10:20]
+    assert len(sub) == 10 and G.same_bits(sub.batch_node_value, v[10:20])
+    idx = torch.tensor([5, 1, 7], device="cuda")
+    assert G.same_bits(f[idx].batch_subtree_size, s[[5, 1, 7]])
+    mask = torch.zeros(3000, dtype=torch.bool); mask[[2, 9]] = True
+    assert len(f[mask]) == 2
+    tr = f[4]
+    assert isinstance(tr, tree.Tree) and G.same_bits(tr.forward(torch.from_numpy(X)), bf[4])
+    assert tr.forward(torch.from_numpy(X[0])).shape == (1,)
+    assert isinstance(tr.to_infix(), str) and len(str(tr)) > 0
+    both = f[0:3] + f[4]
+    assert len(both) == 4 and G.same_bits(both.batch_node_type[3], t[4])
+    g2 = pickle.loads(pickle.dumps(f[0:50]))
+    assert G.same_bits(g2.batch_node_value, v[:50]) and g2.input_len == 3
+    f2 = f[0:5]
+    f2[1] = f[100]
+    assert G.same_bits(f2.batch_node_value[1], v[100])
+    z = tree.Forest.zero_generate(6, 16, 3, 1)
+    assert float(z.SR_fitness(X, y * 0).abs().max()) == 0.0
+
+
+def test_sympy_round_trip(api):
+    tree = api[0]
+    sp = pytest.importorskip("sympy")
+    t = torch.tensor([3, 3, 0, 0, 3, 0, 0, 0], dtype=torch.int16, device="cuda")
+    v = torch.tensor([3, 2, 0, 2, 2, 0, 2, 0], dtype=torch.float32, device="cuda")
+    s = torch.tensor([7, 3, 1, 1, 3, 1, 1, 0], dtype=torch.int16, device="cuda")
+    tr = tree.Tree(3, 1, v, t, s)
+    x0, x2 = sp.symbols("x0 x2")
+    assert sp.simplify(tr.to_sympy_expr() - (x0 - x2) ** 2) == 0
+    assert tr.to_infix() == "((x0 - x2) * (x0 - x2))"
+
+
+def test_operators_through_the_api(api, orc):
+    tree, algorithm = api[0], api[1]
+    torch.manual_seed(1)
+    d = tree.GenerateDescriptor(max_tree_len=32, input_len=3, output_len=1, using_funcs=["+", "-", "*", "/"], max_layer_cnt=5,
+                                const_samples=[-1, 0, 1])
+    f = tree.Forest.random_generate(2000, d)
+    v, t, s = host(f)
+    n = 4000
+    li = torch.randint(0, 2000, (n,), dtype=torch.int32, device="cuda"); ri = torch.randint(0, 2000, (n,), dtype=torch.int32, device="cuda")
+    lp = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda") % f.batch_subtree_size[li.long(), 0]
+    rp = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda") % f.batch_subtree_size[ri.long(), 0]
+    child = f.crossover(li, ri, lp, rp)
+    want = orc.crossover(v, t, s, li.cpu().numpy(), ri.cpu().numpy(), lp.cpu().numpy(), rp.cpu().numpy())
+    for a, b in zip(host(child), want):
+        assert G.same_bits(torch.from_numpy(a), b)
+    donors = tree.Forest.random_generate(2000, d.update(max_layer_cnt=3))
+    pos = torch.randint(0, 1024, (2000,), dtype=torch.int32, device="cuda") % f.batch_subtree_size[:, 0]
+    mut = f.mutate(pos, donors)
+    want = orc.mutate(v, t, s, pos.cpu().numpy(), *host(donors))
+    for a, b in zip(host(mut), want):
+        assert G.same_bits(torch.from_numpy(a), b)
+    # operators of the algorithm package
+    fit = torch.rand(2000, device="cuda")
+    elite, surv = algorithm.DefaultSelection(0.3, elite_rate=0.01)(f, fit)
+    assert elite.dtype == torch.int32 and len(elite) == 20 and len(surv) == 600
+    assert torch.equal(surv[:20], elite) and float(fit[surv.long()].min()) >= float(torch.sort(fit, descending=True).values[599])
+    kids = algorithm.DefaultCrossover()(f, surv, 1980, fit)
+    orc.check_forest(*host(kids), input_len=3)
+    mutated = algorithm.DefaultMutation(0.2, d.update(max_layer_cnt=3))(kids)
+    orc.check_forest(*host(mutated), input_len=3)
+    assert algorithm.DefaultMutation(0.0, d)(kids) is kids
+
+
+def test_gp_loop_xor_improves(api, orc):
+    """configs[0] plumbing (example/basic.py): XOR-3d, pop 5000, max_tree_len 32 — on the GPU path."""
+    tree, algorithm, problem, pipeline = api
+    torch.manual_seed(0)
+    X = torch.tensor([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], dtype=torch.float32, device="cuda")
+    y = (X.sum(dim=1, keepdim=True) % 2).contiguous()
+    prob = problem.SymbolicRegression(datapoints=X, labels=y)
+    d = tree.GenerateDescriptor(max_tree_len=32, input_len=prob.problem_dim, output_len=prob.solution_dim,
+                                using_funcs=["+", "-", "*", "/"], max_layer_cnt=4, const_samples=[-1, 0, 1])
+    algo = algorithm.GeneticProgramming(initial_forest=tree.Forest.random_generate(5000, d), crossover=algorithm.DefaultCrossover(),
+                                        mutation=algorithm.DefaultMutation(0.2, d.update(max_layer_cnt=3)),
+                                        selection=algorithm.DefaultSelection(survival_rate=0.3, elite_rate=0.01),
+                                        enable_pareto_front=True)
+    pipe = pipeline.StandardPipeline(algo, prob, generation_limit=15, is_show_details=False)
+    first = None
+    best_hist = []
+    for _ in range(15):
+        f = pipe.step()
+        first = first if first is not None else float(f[torch.isfinite(f)].max())
+        best_hist.append(float(pipe.best_fitness))
+        orc.check_forest(*host(algo.forest), input_len=3)
+    assert all(b2 >= b1 for b1, b2 in zip(best_hist, best_hist[1:]))      # elitism: never regresses
+    assert best_hist[-1] > first                                             # and selection pressure improves the best
+    best = pipe.best_tree
+    pred = best.forward(X)
+    assert float(((pred - y) ** 2).mean()) == pytest.approx(-best_hist[-1], rel=1e-5, abs=1e-7)
+    pf = algo.pareto_front
+    assert pf.fitness.shape == (32,) and float(pf.fitness.max()) == pytest.approx(best_hist[-1], rel=1e-6)
+    # every recorded front entry has the size of its slot
+    sizes = pf.solution.batch_subtree_size[:, 0]
+    filled = torch.isfinite(pf.fitness)
+    assert torch.equal(sizes[filled].long(), torch.nonzero(filled).squeeze(1))
+    out = pipeline.StandardPipeline(algo, prob, generation_limit=2, is_show_details=False).run()
+    assert isinstance(out, tree.Tree)
+
+
+def test_classification_multi_output(api, orc):
+    tree, _, problem, _ = api
+    torch.manual_seed(2)
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(178, 13)).astype(np.float32)
+    labels = rng.integers(0, 3, 178).astype(np.float32)
+    prob = problem.Classification(datapoints=torch.from_numpy(X).cuda(), labels=torch.from_numpy(labels).cuda(), multi_output=True)
+    assert prob.solution_dim == 3 and prob.problem_dim == 13
+    d = tree.GenerateDescriptor(max_tree_len=128, input_len=13, output_len=3, using_funcs=["+", "-", "*", "/", "sin", "max"],
+                                max_layer_cnt=6, const_samples=[-1, 0, 1], out_prob=0.5)
+    f = tree.Forest.random_generate(1500, d)
+    acc = prob.evaluate(f)
+    got = acc.cpu().numpy()
+    assert got.shape == (1500,) and (got >= 0).all() and (got <= 1).all()
+    # the fused batch_forward feeding it agrees with the oracle ("/" and sin are approximate on the GPU)
+    out = f.batch_forward(prob.datapoints)
+    want = orc.batch_forward(*host(f), X, 3, nthreads=8)
+    G.assert_close_fitness(out, want, rtol=2e-3, atol=1e-5, what="multi-output batch_forward")
+    # and the accuracy is the reference's formula (classification.py:61-66) applied to those outputs
+    prob_t = torch.clip(torch.softmax(torch.from_numpy(want).cuda(), dim=2), 1e-15, 1 - 1e-15)
+    ref_acc = (torch.argmax(prob_t, dim=2) == prob.labels).float().mean(dim=1).cpu().numpy()
+    assert np.mean(np.abs(got - ref_acc) < 1e-6) > 0.97       # approximate ops may flip an argmax here and there
+
+
+def test_evogp_import_shim(api):
+    from evogp.tree import Forest, GenerateDescriptor  # noqa: F401
+    from evogp.algorithm import GeneticProgramming, DefaultSelection, DefaultMutation, DefaultCrossover  # noqa: F401
+    from evogp.problem import SymbolicRegression  # noqa: F401
+    from evogp.pipeline import StandardPipeline  # noqa: F401
+    assert Forest is api[0].Forest
+
+
+def test_host_buffer_entry_point_matches_device_path(native, api):
+    import ctypes
+
+    tree = api[0]
+    torch.manual_seed(5)
+    d = tree.GenerateDescriptor(max_tree_len=64, input_len=3, output_len=1, using_funcs=["+", "-", "*", "/"], max_layer_cnt=6,
+                                const_samples=[-1, 0, 1])
+    f = tree.Forest.random_generate(30000, d)
+    X = torch.rand(1024, 3, device="cuda") * 2 - 1
+    y = (X[:, :1] * X[:, 1:2]).contiguous()
+    dev_fit = f.SR_fitness(X, y).cpu()
+    hv, ht, hs = (a.cpu().pin_memory() for a in (f.batch_node_value, f.batch_node_type, f.batch_subtree_size))
+    hX, hy = X.cpu().pin_memory(), y.cpu().pin_memory()
+    out = torch.empty(30000, dtype=torch.float32).pin_memory()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = native.abi().evogp_SR_fitness_host(30000, 1024, 64, 3, 1, 1, vp(hv), vp(ht), vp(hs), vp(hX), vp(hy), vp(out), torch.cuda.current_device())
+    native.check(rc, "evogp_SR_fitness_host")
+    assert G.same_bits(out, dev_fit.numpy())
+    # pageable host memory works too
+    out2 = torch.empty(30000, dtype=torch.float32)
+    rc = native.abi().evogp_SR_fitness_host(30000, 1024, 64, 3, 1, 1, vp(hv.clone()), vp(ht), vp(hs), vp(hX), vp(hy), vp(out2), torch.cuda.current_device())
+    assert rc == 0 and G.same_bits(out2, dev_fit.numpy())
+    native.abi().evogp_host_release()
