@@ -227,7 +227,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = P_total * N * args.steps / float(e2e_t)
-    h2d = (hi - lo) * L * 8 + N * (V + O) * 4
+    h2d = (hi - lo) * (L * 6 + 2) + N * (V + O) * 4      # value + type rows, one length per tree, dataset
     d2h = (hi - lo) * 4
     fit_host_check = float(np.nanmean(hfit.numpy()))
 

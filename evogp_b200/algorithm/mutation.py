@@ -17,12 +17,14 @@ class DefaultMutation(BaseMutation):
 
     def __call__(self, forest: Forest):
         dev = forest.batch_node_value.device
-        # the reference draws this mask on the CPU generator (default.py:43); keep that stream
-        chosen = torch.rand(forest.pop_size) < self.mutation_rate
-        count = int(chosen.sum())
+        # the reference draws these uniforms on the CPU generator (default.py:43); keep that stream, but do the
+        # comparison on the GPU: the CPU elementwise kernels are multi-threaded and their wake-up costs up to
+        # ~10 ms per call on a many-core host (measured on the B200 box), the H2D of P floats costs ~30 us
+        chosen = torch.rand(forest.pop_size).to(dev, non_blocking=True) < self.mutation_rate
+        rows = chosen.nonzero(as_tuple=True)[0]
+        count = rows.shape[0]
         if count == 0:
             return forest
-        rows = chosen.nonzero(as_tuple=True)[0].to(dev)
         mutants = forest[rows]
         donors = Forest.random_generate(pop_size=count, descriptor=self.descriptor)
         raw = torch.randint(low=0, high=MAX_STACK, size=(count,), dtype=torch.int32, device=dev)

@@ -24,6 +24,10 @@ namespace evogp {
 
 enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_OUTPUT = 2, MODE_ROWWISE = 3 };
 
+int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value, const int16_t *type,
+             const int16_t *size, int len_stride, const float *X, const float *labels, float *out, void *workspace,
+             size_t workspace_bytes, void *stream);
+
 struct ReplayArgs {
     const uint2 *prog;      // [P][Lp]
     unsigned *sched;        // [0] ticket counter
@@ -180,12 +184,23 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                 }
             };
 
-            float acc[K];
-            FOR_K acc[k] = 0.0f;
+            float acc[K], bankB[K], bankC[K];   // accumulator; operand-stack slots 0 and 1 (registers)
+            FOR_K { acc[k] = 0.0f; bankB[k] = 0.0f; bankC[k] = 0.0f; }
             if constexpr (MULTI) {
                 for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
             }
-            int sp = 0, pc = 0;
+            int pc = 0;
+            // operand-stack slots are static (program.cuh): 0 -> bankB, 1 -> bankC, s >= 2 -> shared memory
+            auto slot_store = [&](int slot) {
+                if (slot == 0 && kRegSlots > 0) { FOR_K bankB[k] = acc[k]; }
+                else if (slot == 1 && kRegSlots > 1) { FOR_K bankC[k] = acc[k]; }
+                else st_vec<K>(stack + (slot - kRegSlots) * SLOT + lane_off, acc);
+            };
+            auto slot_load = [&](float(&d)[K], int slot) {
+                if (slot == 0 && kRegSlots > 0) { FOR_K d[k] = bankB[k]; }
+                else if (slot == 1 && kRegSlots > 1) { FOR_K d[k] = bankC[k]; }
+                else ld_vec<K>(d, stack + (slot - kRegSlots) * SLOT + lane_off);
+            };
 
             // ---- generic interpreter: one instruction per call; two stages (operands by form,
             //      then ONE switch over the operator) keep it small enough to stay cache-resident ----
@@ -193,8 +208,8 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                 const uint2 ins = prog[pc];
                 const uint32_t w = ins.x;
                 const float cst = __uint_as_float(ins.y);
-                const uint32_t code = w & 0xFFu, form = code >> 4, op = code & 15u;
-                const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
+                const uint32_t code = w & I_CODE_MASK, form = code >> 4, op = code & 15u;
+                const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDXA_MASK, ib = (w >> I_IDXB_SHIFT) & I_IDXB_MASK;
                 ++pc;
                 if (code == C_END) return true;
                 float x[K], y[K], r[K];
@@ -204,18 +219,16 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                         ++pc;
                         float z[K];
                         if (w & I_IF3_ACONST) { FOR_K x[k] = cst; } else fetch_var(x, ia);
-                        if (w & I_IF3_BCONST) { FOR_K y[k] = __uint_as_float(ext.x); } else fetch_var(y, ext.x & I_IDX_MASK);
-                        if (w & I_IF3_CCONST) { FOR_K z[k] = __uint_as_float(ext.y); } else fetch_var(z, ext.y & I_IDX_MASK);
+                        if (w & I_IF3_BCONST) { FOR_K y[k] = __uint_as_float(ext.x); } else fetch_var(y, ext.x & I_IDXA_MASK);
+                        if (w & I_IF3_CCONST) { FOR_K z[k] = __uint_as_float(ext.y); } else fetch_var(z, ext.y & I_IDXA_MASK);
                         FOR_K r[k] = x[k] > 0.0f ? y[k] : z[k];
                     } else {
                         FOR_K r[k] = 0.0f;
                     }
                 } else {
                     if constexpr (!MULTI) {   // multi-output programs have no operand stack
-                        if (w & I_PUSH) {
-                            st_vec<K>(stack + sp * SLOT + lane_off, acc);
-                            ++sp;
-                        }
+                        const uint32_t push = (w & I_PUSH_MASK) >> I_PUSH_SHIFT;
+                        if (push) slot_store((int)push - 1);
                     }
                     switch (form) {
                     case FM_MISC:
@@ -223,9 +236,8 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                         if (code == C_LOAD_K) { FOR_K acc[k] = cst; return false; }
                         if (code == C_IF) {   // forward.cu:223
                             float t1[K], t2[K];
-                            sp -= 2;
-                            ld_vec<K>(t1, stack + (sp + 1) * SLOT + lane_off);
-                            ld_vec<K>(t2, stack + sp * SLOT + lane_off);
+                            slot_load(t1, (int)ib + 1);   // newer of the two saved values
+                            slot_load(t2, (int)ib);
                             const uint32_t sa = ia & 3, sb = (ia >> 2) & 3, sc = (ia >> 4) & 3;
                             FOR_K {
                                 const float a = sa == 0 ? acc[k] : (sa == 1 ? t1[k] : t2[k]);
@@ -250,8 +262,12 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                     case FM_VV: fetch_var(x, ia); fetch_var(y, ib); break;
                     case FM_VK: fetch_var(x, ia); FOR_K y[k] = cst; break;
                     case FM_KV: FOR_K x[k] = cst; fetch_var(y, ia); break;
-                    case FM_SA: --sp; ld_vec<K>(x, stack + sp * SLOT + lane_off); FOR_K y[k] = acc[k]; break;
-                    case FM_AS: --sp; FOR_K x[k] = acc[k]; ld_vec<K>(y, stack + sp * SLOT + lane_off); break;
+                    case FM_SA: slot_load(x, (int)ia + kRegSlots); FOR_K y[k] = acc[k]; break;
+                    case FM_AS: FOR_K x[k] = acc[k]; slot_load(y, (int)ia + kRegSlots); break;
+                    case FM_BA: FOR_K { x[k] = bankB[k]; y[k] = acc[k]; } break;
+                    case FM_AB: FOR_K { x[k] = acc[k]; y[k] = bankB[k]; } break;
+                    case FM_CA: FOR_K { x[k] = bankC[k]; y[k] = acc[k]; } break;
+                    case FM_AC: FOR_K { x[k] = acc[k]; y[k] = bankC[k]; } break;
                     default: FOR_K { x[k] = 0.0f; y[k] = 0.0f; } break;
                     }
                     if (form <= FM_UK) {
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                     }
                 }
                 if constexpr (MULTI) {   // every instruction of a multi-output program is an OUT node (or its LOAD)
-                    if ((w & I_OUT) && ib != I_IDX_MASK) {
+                    if ((w & I_OUT) && ib != I_IDXB_MASK) {
                         float o_[K];
                         ld_vec<K>(o_, outs + ib * SLOT + lane_off);
                         FOR_K o_[k] += r[k];
@@ -287,20 +303,18 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
             if constexpr (K == 8 && !MULTI && !ROWWISE) {
                 // PTX fast path (fastpath_k8.inc): brx.idx jump table, operands by opcode
                 const uint32_t prog_base = smem_u32(prog), stack_base = smem_u32(stack + lane_off);
-                uint32_t pc_addr = prog_base, sp_addr = stack_base, status;
+                uint32_t pc_addr = prog_base, status;
                 const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
                 for (;;) {
                     asm volatile(EVOGP_FASTPATH_K8_ASM
                                  : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
-                                   "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "+r"(sp_addr), "=r"(status)
-                                 : "r"(xl_addr), "r"(npb)
+                                   "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
+                                 : "r"(xl_addr), "r"(npb), "r"(stack_base)
                                  : "memory");
                     if (status == 0) break;
                     pc = (int)((pc_addr - prog_base) >> 3);
-                    sp = (int)((sp_addr - stack_base) / (SLOT * 4));
                     if (step()) break;
                     pc_addr = prog_base + ((uint32_t)pc << 3);
-                    sp_addr = stack_base + (uint32_t)sp * (SLOT * 4);
                 }
             } else {
                 while (!step()) {
@@ -386,35 +400,34 @@ static inline int prog_pitch(unsigned L) { return (int)((L + 2) & ~1u); }
 
 struct Workspace {
     uint2 *prog;
-    unsigned *sched;   // 4 words
-    unsigned *flags;   // 4 words
+    unsigned *sched;   // 64 words
 };
 static size_t prog_bytes(unsigned P, unsigned L) { return (size_t)P * prog_pitch(L) * sizeof(uint2); }
 static Workspace carve(void *ws, unsigned P, unsigned L) {
     Workspace w;
     unsigned char *b = static_cast<unsigned char *>(ws);
     w.sched = reinterpret_cast<unsigned *>(b);
-    w.flags = w.sched + 4;
     w.prog = reinterpret_cast<uint2 *>(b + 256);
     return w;
 }
 
 template <bool MULTI>
 static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
-                        const int16_t *type, const int16_t *size, int depth, cudaStream_t st) {
-    // threads per CTA limited by the [2][L][T] u32 scratch
+                        const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
+    // threads per CTA limited by the [L][T] scratch (lower.cuh): L = 64 -> 128 threads (48 KB), L = 1024 -> 16 (96 KB)
     int T = 128;
-    while (T > 8 && (size_t)2 * L * T * 4 > 160 * 1024) T >>= 1;   // L = 1024 -> 16 threads (128 KB)
-    const size_t smem = (size_t)2 * L * T * 4;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[MULTI]) {
-        EVOGP_CUDA(cudaFuncSetAttribute(lower_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[MULTI] = true;
+    while (T > 8 && lower_smem_bytes((int)L, T) > 100 * 1024) T >>= 1;
+    const size_t smem = lower_smem_bytes((int)L, T);
+    static size_t attr_set[2] = {0, 0};
+    if (attr_set[MULTI] < smem) {
+        EVOGP_CUDA(cudaFuncSetAttribute(lower_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[MULTI] = smem;
     }
     LowerArgs a;
     a.value = value; a.type = type; a.size = size;
-    a.prog = w.prog; a.sched = w.sched; a.flags = w.flags;
+    a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
+    a.len_stride = len_stride;
     lower_kernel<MULTI><<<(P + T - 1) / T, T, smem, st>>>(a);
     count_launch();
     return check_launch("lower_kernel");
@@ -440,7 +453,8 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     const int SLOT = K * 32;
     a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
     a.NP = a.npass * SLOT;
-    a.depth = depth;
+    a.depth = depth > kRegSlots ? depth - kRegSlots : 1;   // slots 0/1 live in registers
+    depth = a.depth;
     const size_t data = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * a.NP * 4;
     auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
     int warps = 8;
@@ -474,12 +488,12 @@ static int launch_replay(const ReplayArgs &a, int depth, cudaStream_t st) {
     }
 }
 
-static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value,
-                    const int16_t *type, const int16_t *size, const float *X, const float *labels, float *out,
-                    void *workspace, size_t workspace_bytes, void *stream) {
+int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value,
+             const int16_t *type, const int16_t *size, int len_stride, const float *X, const float *labels, float *out,
+             void *workspace, size_t workspace_bytes, void *stream) {
     EVOGP_REQUIRE(P > 0, "popSize must be larger than 0, got %u", P);
     EVOGP_REQUIRE(L > 0 && L <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, L);
-    EVOGP_REQUIRE(V > 0 && V <= 1023, "var_len must be in (0, 1023], got %u", V);
+    EVOGP_REQUIRE(V > 0 && V <= 512, "var_len must be in (0, 512], got %u", V);   // forward.cu:320 asserts the same bound
     EVOGP_REQUIRE(O > 0 && O <= 256, "out_len must be in (0, 256], got %u", O);
     EVOGP_REQUIRE(N > 0, "data_points must be larger than 0, got %u", N);
     EVOGP_REQUIRE((unsigned long long)P * prog_pitch(L) < (1ull << 40), "population too large");
@@ -495,9 +509,8 @@ static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, un
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
-    EVOGP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));   // ticket counter + diagnostics words
-    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, depth, st)
-               : launch_lower<false>(w, P, L, V, O, value, type, size, depth, st);
+    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, st)
+               : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, st);
     if (rc) return rc;
     ReplayArgs a;
     a.prog = w.prog; a.sched = w.sched; a.X = X; a.labels = labels; a.out = out;
@@ -509,6 +522,15 @@ static int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, un
 }  // namespace evogp
 
 using namespace evogp;
+
+// internal (host_api.cu): SR fitness with tree lengths given as a compact int16[popSize] array
+int evogp_sr_fitness_compact_len(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                                 int useMSE, const float *value, const int16_t *type, const int16_t *lengths,
+                                 const float *variables, const float *labels, float *fitnesses, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+    return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type, lengths, 1,
+                    variables, labels, fitnesses, workspace, workspace_bytes, stream);
+}
 
 extern "C" void evogp_eval_set_timing_events(void *begin_event, void *end_event) {
     g_ev_replay_begin = static_cast<cudaEvent_t>(begin_event);
@@ -522,7 +544,7 @@ extern "C" size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen
 extern "C" int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
                               const int16_t *type, const int16_t *subtree_size, const float *variables, float *results,
                               void *workspace, size_t workspace_bytes, void *stream) {
-    return run_eval(MODE_ROWWISE, popSize, 1, maxGPLen, varLen, outLen, value, type, subtree_size, variables, nullptr,
+    return run_eval(MODE_ROWWISE, popSize, 1, maxGPLen, varLen, outLen, value, type, subtree_size, (int)maxGPLen, variables, nullptr,
                     results, workspace, workspace_bytes, stream);
 }
 
@@ -532,13 +554,13 @@ extern "C" int evogp_SR_fitness(unsigned popSize, unsigned dataPoints, unsigned 
                                 void *workspace, size_t workspace_bytes, void *stream) {
     (void)kernel_type;   // reference execute_mode 0..4 (forest.py:340-347): one kernel serves all
     return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
-                    subtree_size, variables, labels, fitnesses, workspace, workspace_bytes, stream);
+                    subtree_size, (int)gpLen, variables, labels, fitnesses, workspace, workspace_bytes, stream);
 }
 
 extern "C" int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,
                                    unsigned outLen, const float *value, const int16_t *type,
                                    const int16_t *subtree_size, const float *variables, float *results,
                                    void *workspace, size_t workspace_bytes, void *stream) {
-    return run_eval(MODE_OUTPUT, popSize, dataPoints, gpLen, varLen, outLen, value, type, subtree_size, variables,
+    return run_eval(MODE_OUTPUT, popSize, dataPoints, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, variables,
                     nullptr, results, workspace, workspace_bytes, stream);
 }

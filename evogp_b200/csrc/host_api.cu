@@ -2,9 +2,17 @@
 // "forest on the host -> fitness on the host" trip a non-torch caller makes.
 // The forest is cut into row chunks that alternate between two streams, so the
 // H2D copy of chunk c+1 overlaps the lowering + replay of chunk c and the D2H of
-// its fitness slice.  Staging buffers are cached across calls.
+// its fitness slice.  Only what the evaluator reads crosses PCIe: node_value and
+// node_type rows plus ONE length per tree (column 0 of subtree_size, gathered on
+// the host into a pinned staging array) — 6 B per node slot instead of 8.
+// Staging buffers are cached across calls.
 #include <mutex>
 #include "common.cuh"
+
+int evogp_sr_fitness_compact_len(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                                 int useMSE, const float *value, const int16_t *type, const int16_t *lengths,
+                                 const float *variables, const float *labels, float *fitnesses, void *workspace,
+                                 size_t workspace_bytes, void *stream);
 
 namespace evogp {
 namespace {
@@ -14,7 +22,9 @@ struct Staging {
     size_t chunk_rows = 0, L = 0;
     float *value[2] = {nullptr, nullptr};
     int16_t *type[2] = {nullptr, nullptr};
-    int16_t *size[2] = {nullptr, nullptr};
+    int16_t *len[2] = {nullptr, nullptr};   // device: one length per tree of the chunk
+    int16_t *host_len = nullptr;            // pinned: lengths of the whole population (column 0 of subtree_size)
+    size_t host_len_cap = 0;
     void *ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0;
     float *fitness[2] = {nullptr, nullptr};
@@ -30,11 +40,12 @@ void release_locked() {
     if (g_st.device < 0) return;
     cudaSetDevice(g_st.device);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(g_st.value[i]); cudaFree(g_st.type[i]); cudaFree(g_st.size[i]);
+        cudaFree(g_st.value[i]); cudaFree(g_st.type[i]); cudaFree(g_st.len[i]);
         cudaFree(g_st.ws[i]); cudaFree(g_st.fitness[i]);
         if (g_st.stream[i]) cudaStreamDestroy(g_st.stream[i]);
     }
     cudaFree(g_st.X); cudaFree(g_st.labels);
+    if (g_st.host_len) cudaFreeHost(g_st.host_len);
     if (g_st.data_ready) cudaEventDestroy(g_st.data_ready);
     g_st = Staging();
 }
@@ -50,7 +61,7 @@ int prepare(int device, size_t rows, size_t L, size_t xbytes, size_t lbytes) {
         for (int i = 0; i < 2; ++i) {
             EVOGP_CUDA(cudaMalloc(&g_st.value[i], rows * L * sizeof(float)));
             EVOGP_CUDA(cudaMalloc(&g_st.type[i], rows * L * sizeof(int16_t)));
-            EVOGP_CUDA(cudaMalloc(&g_st.size[i], rows * L * sizeof(int16_t)));
+            EVOGP_CUDA(cudaMalloc(&g_st.len[i], rows * sizeof(int16_t)));
             EVOGP_CUDA(cudaMalloc(&g_st.ws[i], g_st.ws_bytes));
             EVOGP_CUDA(cudaMalloc(&g_st.fitness[i], rows * sizeof(float)));
             EVOGP_CUDA(cudaStreamCreateWithFlags(&g_st.stream[i], cudaStreamNonBlocking));
@@ -96,6 +107,11 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     if (rc) return rc;
     EVOGP_CUDA(cudaSetDevice(device));
     Staging &s = g_st;
+    if (s.host_len_cap < popSize) {
+        if (s.host_len) cudaFreeHost(s.host_len);
+        EVOGP_CUDA(cudaHostAlloc(&s.host_len, (size_t)popSize * sizeof(int16_t), cudaHostAllocDefault));
+        s.host_len_cap = popSize;
+    }
     EVOGP_CUDA(cudaMemcpyAsync(s.X, variables, xbytes, cudaMemcpyHostToDevice, s.stream[0]));
     EVOGP_CUDA(cudaMemcpyAsync(s.labels, labels, lbytes, cudaMemcpyHostToDevice, s.stream[0]));
     EVOGP_CUDA(cudaEventRecord(s.data_ready, s.stream[0]));
@@ -107,9 +123,10 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
         cudaStream_t st = s.stream[b];
         EVOGP_CUDA(cudaMemcpyAsync(s.value[b], value + r0 * L, nr * L * sizeof(float), cudaMemcpyHostToDevice, st));
         EVOGP_CUDA(cudaMemcpyAsync(s.type[b], type + r0 * L, nr * L * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        EVOGP_CUDA(cudaMemcpyAsync(s.size[b], subtree_size + r0 * L, nr * L * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        rc = evogp_SR_fitness((unsigned)nr, dataPoints, gpLen, varLen, outLen, useMSE, s.value[b], s.type[b], s.size[b],
-                              s.X, s.labels, s.fitness[b], 4, s.ws[b], s.ws_bytes, st);
+        for (size_t r = 0; r < nr; ++r) s.host_len[r0 + r] = subtree_size[(r0 + r) * L];   // the only column the evaluator reads
+        EVOGP_CUDA(cudaMemcpyAsync(s.len[b], s.host_len + r0, nr * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        rc = evogp_sr_fitness_compact_len((unsigned)nr, dataPoints, gpLen, varLen, outLen, useMSE, s.value[b], s.type[b],
+                                          s.len[b], s.X, s.labels, s.fitness[b], s.ws[b], s.ws_bytes, st);
         if (rc) return rc;
         EVOGP_CUDA(cudaMemcpyAsync(fitnesses + r0, s.fitness[b], nr * sizeof(float), cudaMemcpyDeviceToHost, st));
     }

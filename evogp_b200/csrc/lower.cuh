@@ -109,7 +109,7 @@ __host__ __device__ __forceinline__ uint2 mk2(uint32_t a, uint32_t b) {
 // Returns the operand-stack need of the program, or -1 for a malformed row (the program
 // is then {C_NAN, C_END}).
 __host__ __device__ inline int lower_tree_single(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
-                                          int depth_budget, uint2 *out, uint32_t *SA, uint32_t *SB, int stride) {
+                                          int depth_budget, uint2 *out, uint32_t *SA, uint16_t *SB, int stride) {
     bool bad = len < 1 || len > L;
     if (bad) len = 0;
 
@@ -192,15 +192,17 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
             if (Lp > 1) out[1] = mk2(C_END, 0);
             return 0;
         }
-        SB[0] = 0;   // root: start 0, acc not live
+        SB[0] = 0;   // root: start 0, acc not live, stack empty  (start [0:11) | live [11] | height [12:16))
         if (a_ni(r) < Lp) out[a_ni(r)] = mk2(C_END, 0);
     }
     for (int i = 0; i < len; ++i) {
         const uint32_t me = SA[i * stride];
         if (!a_cplx(me)) continue;
-        const uint32_t sb = SB[i * stride];
+        const uint32_t sb = SB[i * stride];   // start [0:11) | live [11] | stack height [12:16)
         const int st = sb & 0x7FF;
-        const uint32_t live_push = ((sb >> 11) & 1) ? I_PUSH : 0;
+        const uint32_t live = (sb >> 11) & 1, height = (sb >> 12) & 0xF;   // stack height when this subtree starts
+        const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
+        const uint32_t height_in = height + live;                            // height once that save has happened
         const int own = st + a_ni(me) - 1;
         const int t = EVOGP_LDG(typ + i);
         const float v = EVOGP_LDG(val + i);
@@ -211,7 +213,7 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
             const int c = i + 1;
             const uint32_t ci = SA[c * stride];
             if (a_cplx(ci)) {
-                SB[c * stride] = sb;    // same start, same liveness
+                SB[c * stride] = (uint16_t)sb;    // same start, same liveness
                 out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
             } else {
                 out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u),
@@ -242,12 +244,18 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
                 const bool x_first = a_need(xi) > a_need(yi);   // ties: right child first, as the reference does
                 const int first = x_first ? x : y, second = x_first ? y : x;
                 const int ni_first = x_first ? a_ni(xi) : a_ni(yi);
-                SB[first * stride] = sb;
-                SB[second * stride] = (uint32_t)(st + ni_first) | (1u << 11);
-                out[own] = mk2((uint32_t)opcode(x_first ? FM_SA : FM_AS, b), 0);
+                SB[first * stride] = (uint16_t)sb;
+                SB[second * stride] = (uint16_t)((uint32_t)(st + ni_first) | (1u << 11) | (height_in << 12));
+                // the first child's value was saved into slot `height_in` by the second child's first instruction
+                int form;
+                uint32_t slot_arg = 0;
+                if (height_in == 0 && kRegSlots > 0) form = x_first ? FM_BA : FM_AB;
+                else if (height_in == 1 && kRegSlots > 1) form = x_first ? FM_CA : FM_AC;
+                else { form = x_first ? FM_SA : FM_AS; slot_arg = (height_in - kRegSlots) << I_IDXA_SHIFT; }
+                out[own] = mk2((uint32_t)opcode(form, b) | slot_arg, 0);
             } else {
                 const int cc = cx ? x : y, lf = cx ? y : x;
-                SB[cc * stride] = sb;
+                SB[cc * stride] = (uint16_t)sb;
                 const Leaf l = leaf_of(EVOGP_LDG(typ + lf), EVOGP_LDG(val + lf), V);
                 out[own] = cx ? leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), l, 0)
                               : leaf_instr(opcode(FM_VA, b), opcode(FM_KA, b), l, 0);
@@ -275,20 +283,22 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int k = j == 0 ? o0 : (j == 1 ? o1 : o2);
-                const uint32_t lv = j == 0 ? ((sb >> 11) & 1) : 1u;
+                const uint32_t lv = j == 0 ? live : 1u;
+                const uint32_t hj = j == 0 ? height : height_in + (uint32_t)(j - 1);   // stack height when entity j starts
                 const uint32_t ik = k == 0 ? inf[0] : (k == 1 ? inf[1] : inf[2]);
                 const int pk = k == 0 ? pos[0] : (k == 1 ? pos[1] : pos[2]);
                 if (a_cplx(ik)) {
-                    SB[pk * stride] = (uint32_t)cur | (lv << 11);
+                    SB[pk * stride] = (uint16_t)((uint32_t)cur | (lv << 11) | (hj << 12));
                     cur += a_ni(ik);
                 } else {
                     out[cur] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ + pk), EVOGP_LDG(val + pk), V),
-                                          lv ? I_PUSH : 0);
+                                          lv ? ((hj + 1) << I_PUSH_SHIFT) : 0);
                     cur += 1;
                 }
                 perm |= (uint32_t)(2 - j) << (2 * k);
             }
-            out[own] = mk2((uint32_t)C_IF | (perm << I_IDXA_SHIFT), 0);
+            // the first two produced values sit in slots height_in (older) and height_in + 1
+            out[own] = mk2((uint32_t)C_IF | (perm << I_IDXA_SHIFT) | (height_in << I_IDXB_SHIFT), 0);
         }
     }
     return root_need;
@@ -335,7 +345,7 @@ __host__ __device__ inline int lower_tree_multi(const float *val, const int16_t 
         const uint32_t bits = f32_bits(EVOGP_LDG(val + i));           // kernel.h:105-113
         const unsigned func = (unsigned)(int)(int16_t)(bits & 0xFFFF);
         const unsigned oi = (unsigned)(int)(int16_t)(bits >> 16);
-        const uint32_t outbits = I_OUT | ((oi < (unsigned)O ? oi : I_IDX_MASK) << I_IDXB_SHIFT);
+        const uint32_t outbits = I_OUT | ((oi < (unsigned)O ? oi : I_IDXB_MASK) << I_IDXB_SHIFT);
         if (slot + 2 > Lp) { bad = true; break; }                     // cannot happen: slots <= nodes
         if (ar == 1) {
             const int u = unary_slot(func);
@@ -369,7 +379,7 @@ __host__ __device__ inline int lower_tree_multi(const float *val, const int16_t 
 
 template <bool MULTI>
 __host__ __device__ inline int lower_tree(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
-                                          int depth_budget, uint2 *out, uint32_t *SA, uint32_t *SB, int stride) {
+                                          int depth_budget, uint2 *out, uint32_t *SA, uint16_t *SB, int stride) {
     if (MULTI) return lower_tree_multi(val, typ, len, L, Lp, V, O, out, SA, stride);
     return lower_tree_single(val, typ, len, L, Lp, V, O, depth_budget, out, SA, SB, stride);
 }
@@ -378,25 +388,30 @@ __host__ __device__ inline int lower_tree(const float *val, const int16_t *typ, 
 struct LowerArgs {
     const float *value;
     const int16_t *type;
-    const int16_t *size;
+    const int16_t *size;   // tree lengths: size[n * len_stride]  (len_stride = L for a packed subtree_size array)
     uint2 *prog;        // [P][Lp]
-    unsigned *sched;    // scheduler words (zeroed by the host before launch)
-    unsigned *flags;    // [0]: count of malformed rows, [1]: max stack need seen
-    int P, L, Lp, V, O, depth_budget;
+    unsigned *sched;    // 64 scheduler words, zeroed here (the replay kernel runs after this one)
+    int P, L, Lp, V, O, depth_budget, len_stride;
 };
+
+// Shared-memory plan of one CTA (T trees, row width L): SA u32 [L][T], SB u16 [L][T] — per-node scratch laid
+// out [node][thread], conflict-free for any mix of node indices.  Rows are read straight from global memory
+// (L2-resident): staging them in shared memory with cp.async was measured SLOWER (158 us vs 84 us at config 2)
+// because the extra 392 B/thread halves the resident warps of this latency-bound, divergent kernel.
+__host__ __device__ inline size_t lower_smem_bytes(int L, int T) { return (size_t)L * T * 6; }
 
 template <bool MULTI>
 __global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
-    extern __shared__ uint32_t scratch[];
+    extern __shared__ __align__(16) uint32_t scratch[];
     const int T = blockDim.x, tid = threadIdx.x;
+    uint32_t *SA = scratch;
+    uint16_t *SB = reinterpret_cast<uint16_t *>(SA + (size_t)g.L * T);
+    if (blockIdx.x == 0 && tid < 64) g.sched[tid] = 0;     // ticket counters of the replay kernel(s) that follow
     const int n = blockIdx.x * T + tid;
     if (n >= g.P) return;
-    const int len = g.size[(size_t)n * g.L];
-    const int need = lower_tree<MULTI>(g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, len, g.L, g.Lp, g.V, g.O,
-                                       g.depth_budget, g.prog + (size_t)n * g.Lp, scratch + tid,
-                                       scratch + (size_t)g.L * T + tid, T);
-    if (need < 0) atomicAdd(g.flags, 1u);
-    else if (need > 0) atomicMax(g.flags + 1, (unsigned)need);
+    const int len = g.size[(size_t)n * g.len_stride];
+    lower_tree<MULTI>(g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, len, g.L, g.Lp, g.V, g.O, g.depth_budget,
+                      g.prog + (size_t)n * g.Lp, SA + tid, SB + tid, T);
 }
 #endif
 

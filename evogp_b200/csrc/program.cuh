@@ -21,22 +21,34 @@ namespace evogp {
 
 // ---------------------------------------------------------------------------
 // instruction word (8 bytes): {header, constant}
-//   header [7:0]   opcode = form * 16 + op      (form and op tables below)
-//          [8]     PUSH    spill acc to the operand stack before executing; only ever set on
-//                          instructions that start a fresh value (LOAD_*, U?V/U?K, VV, VK, KV)
-//          [11]    OUT     multi-output programs only: add the result to outs[idxB]
-//                          (idxB == 0x3FF: output index out of range, result dropped)
-//          [21:12] idxA    variable index of the (first) variable operand; C_IF: operand permutation
-//          [31:22] idxB    variable index of the second variable operand (VV) / output index when OUT
+//   header [8:0]   opcode = form * 16 + op      (form and op tables below)
+//          [12:9]  PUSH    0: nothing; s+1: save acc into operand-stack slot s before executing.
+//                          Only ever set on instructions that start a fresh value
+//                          (LOAD_*, UV/UK, VV, VK, KV).  Multi-output programs never push; there
+//                          bit 9 is OUT (add the result to outs[idxB]) and bits 10-12 are the
+//                          constant flags of C_IF3.
+//          [22:13] idxA    variable index of the (first) variable operand; SA/AS: stack slot - 2;
+//                          C_IF: operand permutation
+//          [31:23] idxB    variable index of the second variable operand (VV); output index when
+//                          OUT (0x1FF: out of range, result dropped); C_IF: lower of its two slots
 //   constant       the constant operand of a *K* form, bit-cast
 // Operand kinds are part of the opcode, so the replay loop never tests a flag to find an operand:
-//   A = accumulator, V = variable (dataset column), K = constant, S = pop from the operand stack.
+//   A accumulator, V variable (dataset column), K constant, B / C operand-stack slots 0 / 1 (held
+//   in registers), S operand-stack slot >= 2 (shared memory).  Slot numbers are static: sibling
+//   order is fixed by the lowering pass, so the stack height at every push and pop is known there
+//   and the replay loop keeps no stack pointer.
 // ---------------------------------------------------------------------------
-constexpr uint32_t I_PUSH = 1u << 8, I_OUT = 1u << 11;
-// C_IF3 (multi-output, three leaf operands) flags which of a, b, c are constants
-constexpr uint32_t I_IF3_BCONST = 1u << 8, I_IF3_ACONST = 1u << 9, I_IF3_CCONST = 1u << 10;
-constexpr int I_IDXA_SHIFT = 12, I_IDXB_SHIFT = 22;
-constexpr uint32_t I_IDX_MASK = 0x3FFu;
+constexpr uint32_t I_CODE_MASK = 0x1FFu;
+constexpr int I_PUSH_SHIFT = 9;
+constexpr uint32_t I_PUSH_MASK = 0xFu << I_PUSH_SHIFT;
+constexpr uint32_t I_OUT = 1u << 9;                                                  // multi-output programs
+constexpr uint32_t I_IF3_ACONST = 1u << 10, I_IF3_BCONST = 1u << 11, I_IF3_CCONST = 1u << 12;
+constexpr int I_IDXA_SHIFT = 13, I_IDXB_SHIFT = 23;
+constexpr uint32_t I_IDXA_MASK = 0x3FFu, I_IDXB_MASK = 0x1FFu;
+// operand-stack slots held in registers (banks B, C).  Measured on B200 (profiles/r1_replay_v3_regbanks.txt):
+// 2 banks cut shared-memory wavefronts by 45 % but cost 25 registers (occupancy 24 -> 16 warps/SM), extra
+// MOV/dispatch work per save and a larger instruction footprint — net slower (479 us vs 309 us) — so 0 for now.
+constexpr int kRegSlots = 0;
 
 constexpr int NUM_U = 16;  // 15 unary functions (ids 14..28) + "unknown id -> 0"
 constexpr int NUM_B = 14;  // 13 binary functions (ids 1..13) + "unknown id -> 0"
@@ -55,9 +67,13 @@ enum : int {
     FM_VV = 8,   // acc = b(var A, var B)
     FM_VK = 9,   // acc = b(var A, const)
     FM_KV = 10,  // acc = b(const, var A)
-    FM_SA = 11,  // acc = b(pop, acc)
-    FM_AS = 12,  // acc = b(acc, pop)
-    FM_COUNT = 13
+    FM_SA = 11,  // acc = b(slot[idxA + 2], acc)
+    FM_AS = 12,  // acc = b(acc, slot[idxA + 2])
+    FM_BA = 13,  // acc = b(B, acc)      slot 0
+    FM_AB = 14,  // acc = b(acc, B)
+    FM_CA = 15,  // acc = b(C, acc)      slot 1
+    FM_AC = 16,  // acc = b(acc, C)
+    FM_COUNT = 17
 };
 // FM_MISC opcodes
 enum : int {
@@ -65,7 +81,7 @@ enum : int {
     C_LOAD_V = 1,  // acc = var A
     C_LOAD_K = 2,  // acc = const
     C_NAN = 3,     // malformed row: result NaN
-    C_IF = 4,      // acc = a > 0 ? b : c; operands are acc / stack top / stack top-1 per idxA
+    C_IF = 4,      // acc = a > 0 ? b : c; operands are acc / slot idxB+1 / slot idxB per idxA
     C_IF3 = 5,     // multi-output only, 2 slots {hdr, a}{b, c}: r = a > 0 ? b : c on three leaf operands
     C_COUNT = FM_COUNT * 16
 };

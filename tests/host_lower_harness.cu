@@ -22,61 +22,72 @@ static int run_row(const float *val, const int16_t *typ, int len, int L, int V, 
                    float *out, int *need_out, int *ninstr_out, int *maxsp_out) {
     const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
-    std::vector<uint32_t> SA(L + 1), SB(L + 1);
+    std::vector<uint32_t> SA(L + 1);
+    std::vector<uint16_t> SB(L + 1);
     const int budget = stack_depth_bound(L);
     const int need = lower_tree<MULTI>(val, typ, len, L, Lp, V, O, budget, prog.data(), SA.data(), SB.data(), 1);
     *need_out = need;
     int ninstr = 0;
-    while (ninstr < Lp && (prog[ninstr].x & 0xFF) != C_END) ++ninstr;
+    while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
     *ninstr_out = ninstr;
     int maxsp = 0;
     std::vector<float> stack(L + 8), outs(O > 0 ? O : 1);
     for (int d = 0; d < N; ++d) {
         const float *x = X + (size_t)d * V;
         float acc = 0.0f;
-        int sp = 0;
+        // operand stack with STATIC slot numbers; `filled` tracks which slots hold a live value so the
+        // harness can verify the lowering pass's bookkeeping (push into a free slot, pop the top one)
+        std::vector<char> filled(L + 8, 0);
+        int height = 0;
         for (int o = 0; o < O; ++o) outs[o] = 0.0f;
         for (int pc = 0; pc < Lp; ++pc) {
             const uint32_t w = prog[pc].x;
             float cst;
             std::memcpy(&cst, &prog[pc].y, 4);
-            const int code = w & 0xFF, form = code >> 4, op = code & 15;
+            const int code = w & I_CODE_MASK, form = code >> 4, op = code & 15;
             if (code == C_END) break;
-            const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDX_MASK, ib = w >> I_IDXB_SHIFT;
+            const uint32_t ia = (w >> I_IDXA_SHIFT) & I_IDXA_MASK, ib = (w >> I_IDXB_SHIFT) & I_IDXB_MASK;
             auto var = [&](uint32_t i) { return x[i < (uint32_t)V ? i : 0]; };
+            auto pop = [&](int slot, float &v) {     // must be the top of the stack
+                if (slot != height - 1 || !filled[slot]) return false;
+                v = stack[slot]; filled[slot] = 0; --height; return true;
+            };
             if (code == C_IF3) {
                 if (!MULTI || pc + 1 >= Lp) return -5;
                 const uint2 ext = prog[++pc];
-                auto leaf = [&](bool is_c, uint32_t word) { float f; std::memcpy(&f, &word, 4); return is_c ? f : var(word & I_IDX_MASK); };
+                auto leaf = [&](bool is_c, uint32_t word) { float f; std::memcpy(&f, &word, 4); return is_c ? f : var(word & I_IDXA_MASK); };
                 const float a = (w & I_IF3_ACONST) ? cst : var(ia);
                 const float b = leaf(w & I_IF3_BCONST, ext.x), c = leaf(w & I_IF3_CCONST, ext.y);
                 const float r = a > 0.0f ? b : c;
-                if (ib != I_IDX_MASK) outs[ib] += r;
+                if (ib != I_IDXB_MASK) outs[ib] += r;
                 acc = r;
                 continue;
             }
-            if (!MULTI && (w & I_PUSH)) {
-                if (!(code == C_LOAD_V || code == C_LOAD_K || form == FM_UV || form == FM_UK || form == FM_VV ||
-                      form == FM_VK || form == FM_KV)) return -6;   // PUSH only on fresh-value instructions
-                stack[sp++] = acc;
-                if (sp > maxsp) maxsp = sp;
+            if (!MULTI) {
+                const int push = (w & I_PUSH_MASK) >> I_PUSH_SHIFT;
+                if (push) {
+                    if (!(code == C_LOAD_V || code == C_LOAD_K || form == FM_UV || form == FM_UK || form == FM_VV ||
+                          form == FM_VK || form == FM_KV)) return -6;   // PUSH only on fresh-value instructions
+                    if (push - 1 != height || filled[push - 1]) return -7;   // static slot == dynamic height
+                    stack[push - 1] = acc; filled[push - 1] = 1; ++height;
+                    if (height > maxsp) maxsp = height;
+                }
             }
             if (code == C_LOAD_V) { acc = var(ia); continue; }
             if (code == C_LOAD_K) { acc = cst; continue; }
             if (code == C_NAN) { acc = NAN; for (int o = 0; o < O; ++o) outs[o] = NAN; continue; }
             float r;
             if (code == C_IF) {
-                sp -= 2;
-                if (sp < 0) return -2;
-                const float t1 = stack[sp + 1], t2 = stack[sp];
+                float t1, t2;
+                if (!pop((int)ib + 1, t1) || !pop((int)ib, t2)) return -2;
                 auto pick = [&](uint32_t s) { return s == 0 ? acc : (s == 1 ? t1 : t2); };
                 const float a = pick(ia & 3), b = pick((ia >> 2) & 3), c = pick((ia >> 4) & 3);
                 r = a > 0.0f ? b : c;
             } else if (form >= FM_UA && form <= FM_UK) {
                 const float a = form == FM_UA ? acc : (form == FM_UV ? var(ia) : cst);
                 r = oracle_apply_unary(op + F_SIN, a);
-            } else if (form >= FM_AV && form <= FM_AS) {
-                float a, b;
+            } else if (form >= FM_AV && form <= FM_AC) {
+                float a, b, s;
                 switch (form) {
                 case FM_AV: a = acc; b = var(ia); break;
                 case FM_AK: a = acc; b = cst; break;
@@ -85,17 +96,21 @@ static int run_row(const float *val, const int16_t *typ, int len, int L, int V, 
                 case FM_VV: a = var(ia); b = var(ib); break;
                 case FM_VK: a = var(ia); b = cst; break;
                 case FM_KV: a = cst; b = var(ia); break;
-                case FM_SA: if (--sp < 0) return -2; a = stack[sp]; b = acc; break;
-                default: if (--sp < 0) return -2; a = acc; b = stack[sp]; break;   // FM_AS
+                case FM_SA: if (!pop((int)ia + kRegSlots, s)) return -2; a = s; b = acc; break;
+                case FM_AS: if (!pop((int)ia + kRegSlots, s)) return -2; a = acc; b = s; break;
+                case FM_BA: if (kRegSlots < 1 || !pop(0, s)) return -2; a = s; b = acc; break;
+                case FM_AB: if (kRegSlots < 1 || !pop(0, s)) return -2; a = acc; b = s; break;
+                case FM_CA: if (kRegSlots < 2 || !pop(1, s)) return -2; a = s; b = acc; break;
+                default: if (kRegSlots < 2 || !pop(1, s)) return -2; a = acc; b = s; break;   // FM_AC
                 }
                 r = oracle_apply_binary(op + F_ADD, a, b);
             } else {
                 return -3;
             }
-            if (MULTI && (w & I_OUT) && ib != I_IDX_MASK) outs[ib] += r;
+            if (MULTI && (w & I_OUT) && ib != I_IDXB_MASK) outs[ib] += r;
             acc = r;
         }
-        if (sp != 0) return -4;
+        if (height != 0) return -4;
         if (MULTI) for (int o = 0; o < O; ++o) out[(size_t)d * O + o] = outs[o];
         else out[d] = acc;
     }
