@@ -5,8 +5,10 @@
 // (:304-351, :402-479, :591-647, :738-779), and fuses Forest.batch_forward
 // (tree/forest.py:143-176).
 //
-// Two kernels:
-//   lower_kernel  (lower.cuh)  packed rows -> accumulator-machine programs, 8 B/slot
+// Two kernels (a single fused kernel — each warp lowering its own tree into shared memory before replaying
+// it — was built and measured: same total time at best, because lowering + replay code together overflow the
+// SM instruction cache: sm__icc_request_hit_rate 97 % -> 70 %, profiles/r1_fused_kernel_icache.txt):
+//   lower_kernel  (lower.cuh)  packed rows -> accumulator-machine programs, 8 B/slot; one warp per tree
 //   replay_kernel (here)       persistent CTAs; each WARP owns one tree at a time,
 //        lanes own datapoints (K per lane, float4-vectorised), so the opcode
 //        dispatch is warp-uniform.  The next tree's program row is pulled into
@@ -27,6 +29,8 @@ enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_OUTPUT = 2, MODE_ROWWISE = 3 };
 int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value, const int16_t *type,
              const int16_t *size, int len_stride, const float *X, const float *labels, float *out, void *workspace,
              size_t workspace_bytes, void *stream);
+
+
 
 struct ReplayArgs {
     const uint2 *prog;      // [P][Lp]
@@ -414,12 +418,13 @@ static Workspace carve(void *ws, unsigned P, unsigned L) {
 template <bool MULTI>
 static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
                         const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
-    // threads per CTA limited by the [L][T] scratch (lower.cuh): L = 64 -> 128 threads (48 KB), L = 1024 -> 16 (96 KB)
-    int T = 128;
-    while (T > 8 && lower_smem_bytes((int)L, T) > 100 * 1024) T >>= 1;
-    const size_t smem = lower_smem_bytes((int)L, T);
+    // one warp per tree; per-warp scratch is 18 B per node slot (lower.cuh)
+    const size_t per_warp = (lower_scratch_bytes((int)L) + 15) & ~(size_t)15;
+    int warps = 8;
+    while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
+    const size_t smem = warps * per_warp;
     static size_t attr_set[2] = {0, 0};
-    if (attr_set[MULTI] < smem) {
+    if (smem > 48 * 1024 && attr_set[MULTI] < smem) {
         EVOGP_CUDA(cudaFuncSetAttribute(lower_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[MULTI] = smem;
     }
@@ -427,8 +432,11 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
     a.value = value; a.type = type; a.size = size;
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
-    a.len_stride = len_stride;
-    lower_kernel<MULTI><<<(P + T - 1) / T, T, smem, st>>>(a);
+    a.rows_have_sizes = len_stride != 1;
+    long long grid = ((long long)P + warps - 1) / warps;
+    const long long cap = (long long)g_sm_count * (2048 / (warps * 32));
+    if (grid > cap) grid = cap;
+    lower_kernel<MULTI><<<(unsigned)grid, warps * 32, smem, st>>>(a);
     count_launch();
     return check_launch("lower_kernel");
 }

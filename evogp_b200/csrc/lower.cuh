@@ -1,14 +1,18 @@
 // lower.cuh — lowering pass: packed prefix row -> accumulator-machine program.
-// One thread per tree (the pass is two O(len) dependent scans); per-node scratch
-// lives in shared memory laid out [node][thread] so any mix of node indices across
-// a warp is bank-conflict free.
 //
-// Structure is derived exactly the way the reference's evaluator derives it
-// (forward.cu:277-296): from node types and subtree_size[0] only; interior
-// subtree_size entries are recomputed, not trusted.
+// One WARP per tree, lanes over NODES.  The pass is a short sequence of data-parallel phases
+// over the row (classify, prefix-sum the instruction slots, rank siblings, propagate slot
+// offsets / stack heights root -> leaves, emit), so it has no divergence between trees and no
+// per-thread serial scans.  (The first version ran one thread per tree with two dependent
+// O(len) scans: latency-bound and divergent, ~140 us for 1e5 trees; see DESIGN.md.)
 //
-// lower_tree() is __host__ __device__ so that tests/host_lower_harness.cu can run the
-// very same code on the CPU and replay its output against the oracle.
+// Structure comes from node types and subtree_size; the sizes are verified against the arities
+// and recomputed by one lane when they do not match (the reference's evaluator reads only
+// subtree_size[0], forward.cu:283, so a row with stale interior sizes must still evaluate).
+//
+// Everything is written against a tiny lane abstraction (Lanes) so that
+// tests/host_lower_harness.cu runs the very same source serially on the CPU and replays its
+// output against the oracle.
 #pragma once
 #include "program.cuh"
 
@@ -51,15 +55,6 @@ __host__ __device__ __forceinline__ int f32_to_i32(float v) {
 }
 __host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
-
-// scratch word A: subtree size [0:11) | instruction slots [11:22) | stack need [22:30) | complex [31]
-__host__ __device__ __forceinline__ uint32_t packA(int sz, int ni, int need, int cplx) {
-    return (uint32_t)sz | ((uint32_t)ni << 11) | ((uint32_t)need << 22) | ((uint32_t)cplx << 31);
-}
-__host__ __device__ __forceinline__ int a_sz(uint32_t a) { return a & 0x7FF; }
-__host__ __device__ __forceinline__ int a_ni(uint32_t a) { return (a >> 11) & 0x7FF; }
-__host__ __device__ __forceinline__ int a_need(uint32_t a) { return (a >> 22) & 0xFF; }
-__host__ __device__ __forceinline__ int a_cplx(uint32_t a) { return a >> 31; }
 
 template <bool MULTI>
 __host__ __device__ __forceinline__ int node_arity(int t) {
@@ -105,132 +100,330 @@ __host__ __device__ __forceinline__ uint2 mk2(uint32_t a, uint32_t b) {
     return r;
 }
 
-// Lowers one row.  SA/SB: two scratch arrays of `len` words, element i at [i * stride].
-// Returns the operand-stack need of the program, or -1 for a malformed row (the program
-// is then {C_NAN, C_END}).
-__host__ __device__ inline int lower_tree_single(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
-                                          int depth_budget, uint2 *out, uint32_t *SA, uint16_t *SB, int stride) {
-    bool bad = len < 1 || len > L;
-    if (bad) len = 0;
 
-    // ---- pass A: leaves -> root.  size, slot count, Sethi-Ullman need per subtree ----
-    for (int i = len - 1; i >= 0 && !bad; --i) {
-        const int t = EVOGP_LDG(typ + i);
-        const int ar = node_arity<false>(t);
-        if (ar == 0) {
-            SA[i * stride] = packA(1, 0, 0, 0);
-            continue;
-        }
-        int c = i + 1, sz = 1;
-        uint32_t ch[3] = {0, 0, 0};
+// ---------------------------------------------------------------------------
+// lane abstraction: device = a warp (lane, 32), host = one "lane" doing everything
+// ---------------------------------------------------------------------------
+struct Lanes {
+    int lane, n;
+};
+__host__ __device__ __forceinline__ void lanes_sync() {
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+}
+__host__ __device__ __forceinline__ bool lanes_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p);
+#else
+    return p;
+#endif
+}
+__host__ __device__ __forceinline__ int lanes_max(int v) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (k < ar && !bad) {
-                if (c >= len) {
-                    bad = true;
-                } else {
-                    ch[k] = SA[c * stride];
-                    c += a_sz(ch[k]);
-                    sz += a_sz(ch[k]);
-                }
-            }
-        }
-        if (bad) break;
-        int ni, need;
-        if (ar == 1) {
-            ni = 1 + (a_cplx(ch[0]) ? a_ni(ch[0]) : 0);
-            need = a_cplx(ch[0]) ? a_need(ch[0]) : 0;
-        } else if (ar == 2) {
-            const int cx = a_cplx(ch[0]), cy = a_cplx(ch[1]);
-            if (!cx && !cy) {
-                const bool both_const = (EVOGP_LDG(typ + i + 1) & NT_MASK) == NT_CONST &&
-                                        (EVOGP_LDG(typ + i + 2) & NT_MASK) == NT_CONST;
-                ni = both_const ? 2 : 1;
-                need = 0;
-            } else if (cx && cy) {
-                const int nx = a_need(ch[0]), ny = a_need(ch[1]);
-                ni = a_ni(ch[0]) + a_ni(ch[1]) + 1;
-                need = imax(imax(nx, ny), imin(nx, ny) + 1);
-            } else {
-                const uint32_t cc = cx ? ch[0] : ch[1];
-                ni = a_ni(cc) + 1;
-                need = a_need(cc);
-            }
-        } else {
-            // ternary: every child (leaf or not) is produced as a value: leaf = one C_LOAD slot, need 0
-            int nd[3], tot = 1;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+    return v;
+}
+// in-place exclusive prefix sum of a[0..n) (u16), a[n] = total
+__host__ __device__ inline void lanes_exclusive_scan(Lanes ln, uint16_t *a, int n) {
+#ifdef __CUDA_ARCH__
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + ln.lane;
+        const int x = j < n ? a[j] : 0;
+        int incl = x;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                nd[k] = a_cplx(ch[k]) ? a_need(ch[k]) : 0;
-                tot += a_cplx(ch[k]) ? a_ni(ch[k]) : 1;
-            }
-            const int hi = imax(nd[0], imax(nd[1], nd[2])), lo = imin(nd[0], imin(nd[1], nd[2]));
-            const int mid = nd[0] + nd[1] + nd[2] - hi - lo;
-            ni = tot;
-            need = imax(hi, imax(mid + 1, lo + 2));
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln.lane >= o) incl += y;
         }
-        SA[i * stride] = packA(sz, ni, need, 1);
+        if (j < n) a[j] = (uint16_t)(carry + incl - x);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    int root_need = 0;
-    if (!bad && len > 0) {
-        const uint32_t r = SA[0];
-        root_need = a_cplx(r) ? a_need(r) : 0;
-        if (a_sz(r) != len) bad = true;                  // prefix does not close at len
-        else if (root_need > depth_budget) bad = true;   // cannot happen (stack_depth_bound)
+    if (ln.lane == 0) a[n] = (uint16_t)carry;
+    __syncwarp();
+#else
+    int carry = 0;
+    for (int j = 0; j < n; ++j) {
+        const int x = a[j];
+        a[j] = (uint16_t)carry;
+        carry += x;
     }
-    if (bad || len == 0) {
+    a[n] = (uint16_t)carry;
+#endif
+}
+
+__host__ __device__ __forceinline__ void lanes_atomic_add(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+// in-place inclusive prefix sum of a[0..n) (u32, wrap-around arithmetic)
+__host__ __device__ inline void lanes_inclusive_scan32(Lanes ln, uint32_t *a, int n) {
+#ifdef __CUDA_ARCH__
+    uint32_t carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + ln.lane;
+        uint32_t incl = j < n ? a[j] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln.lane >= o) incl += y;
+        }
+        if (j < n) a[j] = carry + incl;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+#else
+    uint32_t carry = 0;
+    for (int j = 0; j < n; ++j) {
+        carry += a[j];
+        a[j] = carry;
+    }
+#endif
+}
+
+// per-tree scratch (one warp): arrays of L entries (M: L + 1).  In the fused kernel t/v/s are the TMA row buffer
+// and the rest aliases the (idle) operand-stack area.
+struct LowerScratch {
+    int16_t *t;      // node types
+    uint32_t *v;     // node value bits
+    uint16_t *s;     // subtree sizes
+    uint16_t *M;     // marks -> exclusive prefix sum of instruction slots
+    uint32_t *D;     // path-sum workspace: [L + 1]
+    uint16_t *q;     // value children: rank [0:2) | slots emitted before this child among its siblings [2:13) | valid [15]
+    uint16_t *st;    // start slot [0:11) | acc live [11] | stack height [12:16)
+};
+__host__ __device__ inline size_t lower_scratch_bytes(int L) { return (size_t)L * 18 + 32; }   // 4+2+2 rows, 2+4+2+2 aux
+// the part that is not the staged rows: M, D, q, st
+__host__ __device__ inline size_t lower_aux_bytes(int L) { return (size_t)L * 10 + 32; }
+__host__ __device__ inline LowerScratch carve_aux(void *rows_v, void *rows_t, void *rows_s, void *aux, int L) {
+    LowerScratch k;
+    k.v = static_cast<uint32_t *>(rows_v);
+    k.t = static_cast<int16_t *>(rows_t);
+    k.s = static_cast<uint16_t *>(rows_s);
+    unsigned char *b = static_cast<unsigned char *>(aux);
+    k.D = reinterpret_cast<uint32_t *>(b);                 b += (size_t)(L + 1) * 4;
+    k.M = reinterpret_cast<uint16_t *>(b);                 b += (size_t)(L + 1) * 2 + 2;
+    k.q = reinterpret_cast<uint16_t *>(b);                 b += (size_t)L * 2;
+    k.st = reinterpret_cast<uint16_t *>(b);
+    return k;
+}
+__host__ __device__ inline LowerScratch carve_scratch(void *mem, int L) {
+    LowerScratch k;
+    unsigned char *b = static_cast<unsigned char *>(mem);
+    k.v = reinterpret_cast<uint32_t *>(b);                 b += (size_t)L * 4;
+    k.t = reinterpret_cast<int16_t *>(b);                  b += (size_t)L * 2;
+    k.s = reinterpret_cast<uint16_t *>(b);                 b += (size_t)L * 2;
+    k.D = reinterpret_cast<uint32_t *>(b);                 b += (size_t)(L + 1) * 4;
+    k.M = reinterpret_cast<uint16_t *>(b);                 b += (size_t)(L + 1) * 2 + 2;   // keeps 4-byte multiples
+    k.q = reinterpret_cast<uint16_t *>(b);                 b += (size_t)L * 2;
+    k.st = reinterpret_cast<uint16_t *>(b);
+    return k;
+}
+
+__host__ __device__ __forceinline__ int arity_of(int t, bool multi) {
+    if (multi) t &= NT_MASK;   // single-output mode does not mask (forward.cu:91-94)
+    return (t == NT_VAR || t == NT_CONST) ? 0 : (t == NT_UFUNC ? 1 : (t == NT_BFUNC ? 2 : 3));
+}
+__host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// Stage the row and make sure s[] holds arity-consistent subtree sizes.  Returns false for a malformed row.
+// val == nullptr: the rows are already staged in k.t / k.v (/ k.s) — the fused kernel's TMA path.
+// size == nullptr with val != nullptr, or have_sizes == false: no size row; sizes are recomputed from the arities.
+template <bool MULTI>
+__host__ __device__ inline bool lower_stage(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
+                                            int L, LowerScratch k, bool have_sizes) {
+    if (len < 1 || len > L) return false;
+    if (val) {
+        for (int j = ln.lane; j < len; j += ln.n) {
+            k.t[j] = EVOGP_LDG(typ + j);
+            k.v[j] = f32_bits(EVOGP_LDG(val + j));
+            k.s[j] = (size && have_sizes) ? (uint16_t)EVOGP_LDG(size + j) : (uint16_t)0;
+        }
+    } else if (!have_sizes) {
+        for (int j = ln.lane; j < len; j += ln.n) k.s[j] = 0;
+    }
+    lanes_sync();
+    // verify: every function node's size is 1 + its children's, children stay inside the row, root spans it
+    bool bad = false;
+    for (int j = ln.lane; j < len; j += ln.n) {
+        const int ar = arity_of(k.t[j], MULTI);
+        int c = j + 1, tot = 1;
+        for (int a = 0; a < ar && !bad; ++a) {
+            if (c >= len) { bad = true; break; }
+            const int cs = k.s[c];
+            if (cs < 1) bad = true;
+            tot += cs;
+            c += cs;
+        }
+        if ((int)k.s[j] != tot || j + tot > len) bad = true;
+    }
+    if (ln.lane == 0 && (int)k.s[0] != len) bad = true;
+    if (!lanes_any(bad)) return true;
+    // stale or inconsistent sizes: recompute them from the arities, leaves -> root (one lane; rare)
+    bool ok = true;
+    if (ln.lane == 0) {
+        for (int i = len - 1; i >= 0 && ok; --i) {
+            const int ar = arity_of(k.t[i], MULTI);
+            int c = i + 1, tot = 1;
+            for (int a = 0; a < ar; ++a) {
+                if (c >= len) { ok = false; break; }
+                tot += k.s[c];
+                c += k.s[c];
+            }
+            k.s[i] = (uint16_t)tot;
+        }
+        if (ok && (int)k.s[0] != len) ok = false;   // the prefix does not close at len
+    }
+    lanes_sync();
+    return !lanes_any(!ok);
+}
+
+__host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
+    if (ln.lane == 0) {
         out[0] = mk2(C_NAN, 0);
         if (Lp > 1) out[1] = mk2(C_END, 0);
+    }
+}
+
+// Single-output rows.  Returns the operand-stack height the program needs, or -1 for a malformed row.
+__host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
+                                                 int len, int L, int Lp, int V, int depth_budget, uint2 *out,
+                                                 LowerScratch k, bool have_sizes) {
+    if (!lower_stage<false>(ln, val, typ, size, len, L, k, have_sizes)) {
+        emit_nan(ln, out, Lp);
         return -1;
     }
-
-    // ---- pass B: root -> leaves.  place each subtree's slot range, emit instructions ----
-    {
-        const uint32_t r = SA[0];
-        if (!a_cplx(r)) {   // the tree is a single leaf
-            out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ), EVOGP_LDG(val), V), 0);
+    auto is_func = [&](int j) { return arity_of(k.t[j], false) != 0; };
+    auto is_const = [&](int j) { return (k.t[j] & NT_MASK) == NT_CONST; };
+    if (!is_func(0)) {   // the tree is a single leaf
+        if (ln.lane == 0) {
+            out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[0], bits_f32(k.v[0]), V), 0);
             if (Lp > 1) out[1] = mk2(C_END, 0);
-            return 0;
         }
-        SB[0] = 0;   // root: start 0, acc not live, stack empty  (start [0:11) | live [11] | height [12:16))
-        if (a_ni(r) < Lp) out[a_ni(r)] = mk2(C_END, 0);
+        return 0;
     }
-    for (int i = 0; i < len; ++i) {
-        const uint32_t me = SA[i * stride];
-        if (!a_cplx(me)) continue;
-        const uint32_t sb = SB[i * stride];   // start [0:11) | live [11] | stack height [12:16)
-        const int st = sb & 0x7FF;
-        const uint32_t live = (sb >> 11) & 1, height = (sb >> 12) & 0xF;   // stack height when this subtree starts
-        const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
-        const uint32_t height_in = height + live;                            // height once that save has happened
-        const int own = st + a_ni(me) - 1;
-        const int t = EVOGP_LDG(typ + i);
-        const float v = EVOGP_LDG(val + i);
-        const int ar = node_arity<false>(t);
-        const unsigned func = f32_to_u32(v);         // forward.cu:108 `(unsigned int)node_value`
-        if (ar == 1) {
-            const int u = unary_slot(func);
-            const int c = i + 1;
-            const uint32_t ci = SA[c * stride];
-            if (a_cplx(ci)) {
-                SB[c * stride] = (uint16_t)sb;    // same start, same liveness
-                out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
-            } else {
-                out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u),
-                                      leaf_of(EVOGP_LDG(typ + c), EVOGP_LDG(val + c), V), live_push);
+    // ---- marks: instruction slots each node contributes itself ----
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int ar = arity_of(k.t[i], false);
+        int m = 0;
+        if (ar == 1) m = 1;
+        else if (ar == 2) {
+            const int x = i + 1, y = x + k.s[x];
+            m = (!is_func(x) && !is_func(y) && is_const(x) && is_const(y)) ? 2 : 1;   // two constants: LOAD + AK
+        } else if (ar == 3) {
+            const int a = i + 1, b = a + k.s[a], c = b + k.s[b];
+            m = 1 + (!is_func(a)) + (!is_func(b)) + (!is_func(c));                     // every leaf child is a LOAD
+        }
+        k.M[i] = (uint16_t)m;
+        k.q[i] = 0;
+    }
+    lanes_sync();
+    lanes_exclusive_scan(ln, k.M, len);
+    auto ni = [&](int j) { return (int)k.M[j + k.s[j]] - (int)k.M[j]; };   // slots of the whole subtree j
+    // ---- rank the value-producing children of every function node: larger subtree first
+    //      (ties: later child first, the reference's order), so the lighter sibling is the one evaluated
+    //      with a value pending and the operand stack stays O(log len) deep (stack_depth_bound) ----
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int ar = arity_of(k.t[i], false);
+        if (ar == 0) continue;
+        int c[3], n = 0;
+        c[0] = i + 1;
+        if (ar > 1) c[1] = c[0] + k.s[c[0]];
+        if (ar > 2) c[2] = c[1] + k.s[c[1]];
+        if (ar == 3) {
+            int o0 = 2, o1 = 1, o2 = 0;   // c, b, a; stable bubble sort by size, descending
+            if (k.s[c[o1]] > k.s[c[o0]]) { const int sw = o0; o0 = o1; o1 = sw; }
+            if (k.s[c[o2]] > k.s[c[o1]]) { const int sw = o1; o1 = o2; o2 = sw; }
+            if (k.s[c[o1]] > k.s[c[o0]]) { const int sw = o0; o0 = o1; o1 = sw; }
+            const int ord[3] = {o0, o1, o2};
+            int before = 0;
+            for (int r = 0; r < 3; ++r) {
+                const int ch = ord[r] == 0 ? c[0] : (ord[r] == 1 ? c[1] : c[2]);
+                k.q[ch] = (uint16_t)(r | (before << 2) | 0x8000);
+                before += is_func(ch) ? ni(ch) : 1;
             }
+        } else {
+            for (int a = 0; a < ar; ++a)
+                if (is_func(c[a])) ++n;
+            if (ar == 1) {
+                if (n) k.q[c[0]] = 0x8000;
+            } else if (n == 1) {
+                const int ch = is_func(c[0]) ? c[0] : c[1];
+                k.q[ch] = 0x8000;
+            } else if (n == 2) {
+                const bool x_first = k.s[c[0]] > k.s[c[1]];
+                const int first = x_first ? c[0] : c[1], second = x_first ? c[1] : c[0];
+                k.q[first] = 0x8000;
+                k.q[second] = (uint16_t)(1 | (ni(first) << 2) | 0x8000);
+            }
+        }
+    }
+    // ---- root -> leaves in one prefix sum.  For a value child j (rank r, `before` slots emitted ahead of it
+    //      among its siblings):  start(j) = sum of `before` over the path root..j;  pending(j) = sum of r over
+    //      that path = values alive (in acc or on the stack) when subtree j begins, so acc is live iff
+    //      pending > 0 and the stack height is pending - 1.  A path sum in prefix order is a prefix sum of
+    //      "add at i, subtract at i + size[i]" (i's contribution covers exactly its subtree span). ----
+    for (int i = ln.lane; i <= len; i += ln.n) k.D[i] = 0;
+    lanes_sync();
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const uint32_t qq = k.q[i];
+        if (!(qq & 0x8000)) continue;
+        const uint32_t add = ((qq >> 2) & 0x7FF) | ((qq & 3) << 16);    // before | rank << 16
+        if (add) {
+            lanes_atomic_add(&k.D[i], add);
+            lanes_atomic_add(&k.D[i + k.s[i]], 0u - add);
+        }
+    }
+    lanes_sync();
+    lanes_inclusive_scan32(ln, k.D, len);
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const uint32_t d = k.D[i], pending = d >> 16;
+        const uint32_t live = pending ? 1u : 0u, h = pending ? pending - 1 : 0u;
+        k.st[i] = (uint16_t)((d & 0x7FF) | (live << 11) | (h << 12));
+    }
+    lanes_sync();
+    // ---- emit ----
+    int my_max = 0;
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int ar = arity_of(k.t[i], false);
+        const bool valued = i == 0 || (k.q[i] & 0x8000);
+        if (!valued) continue;                    // folded leaf: an operand of its parent
+        const uint32_t sb = k.st[i];
+        const int st = sb & 0x7FF;
+        const uint32_t live = (sb >> 11) & 1, height = (sb >> 12) & 0xF;
+        const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
+        const uint32_t height_in = height + live;
+        if (live) my_max = my_max > (int)height + 1 ? my_max : (int)height + 1;
+        if (ar == 0) {                            // leaf child of a ternary node: produced by a LOAD
+            out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[i], bits_f32(k.v[i]), V), live_push);
+            continue;
+        }
+        const int own = st + ni(i) - 1;
+        const unsigned func = f32_to_u32(bits_f32(k.v[i]));   // forward.cu:108 `(unsigned int)node_value`
+        if (ar == 1) {
+            const int u = unary_slot(func), c = i + 1;
+            if (is_func(c)) out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
+            else out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u), leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
         } else if (ar == 2) {
-            const int b = binary_slot(func);
-            const int x = i + 1;
-            const uint32_t xi = SA[x * stride];
-            const int y = x + a_sz(xi);
-            const uint32_t yi = SA[y * stride];
-            const int cx = a_cplx(xi), cy = a_cplx(yi);
+            const int b = binary_slot(func), x = i + 1, y = x + k.s[x];
+            const bool cx = is_func(x), cy = is_func(y);
             if (!cx && !cy) {
-                const int tx = EVOGP_LDG(typ + x), ty = EVOGP_LDG(typ + y);
-                const float vx = EVOGP_LDG(val + x), vy = EVOGP_LDG(val + y);
-                const Leaf lx = leaf_of(tx, vx, V), ly = leaf_of(ty, vy, V);
-                if (a_ni(me) == 2) {          // two constants: load the first, then acc (op) const
+                const Leaf lx = leaf_of(k.t[x], bits_f32(k.v[x]), V), ly = leaf_of(k.t[y], bits_f32(k.v[y]), V);
+                if (lx.is_const && ly.is_const) {          // two constants: load the first, then acc (op) const
                     out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, lx, live_push);
                     out[st + 1] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), ly, 0);
                 } else if (!lx.is_const && !ly.is_const) {
@@ -241,11 +434,7 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
                     out[own] = mk2((uint32_t)opcode(FM_KV, b) | live_push | (ly.bits << I_IDXA_SHIFT), lx.bits);
                 }
             } else if (cx && cy) {
-                const bool x_first = a_need(xi) > a_need(yi);   // ties: right child first, as the reference does
-                const int first = x_first ? x : y, second = x_first ? y : x;
-                const int ni_first = x_first ? a_ni(xi) : a_ni(yi);
-                SB[first * stride] = (uint16_t)sb;
-                SB[second * stride] = (uint16_t)((uint32_t)(st + ni_first) | (1u << 11) | (height_in << 12));
+                const bool x_first = (k.q[x] & 3) == 0;
                 // the first child's value was saved into slot `height_in` by the second child's first instruction
                 int form;
                 uint32_t slot_arg = 0;
@@ -253,165 +442,127 @@ __host__ __device__ inline int lower_tree_single(const float *val, const int16_t
                 else if (height_in == 1 && kRegSlots > 1) form = x_first ? FM_CA : FM_AC;
                 else { form = x_first ? FM_SA : FM_AS; slot_arg = (height_in - kRegSlots) << I_IDXA_SHIFT; }
                 out[own] = mk2((uint32_t)opcode(form, b) | slot_arg, 0);
+                my_max = my_max > (int)height_in + 1 ? my_max : (int)height_in + 1;
             } else {
-                const int cc = cx ? x : y, lf = cx ? y : x;
-                SB[cc * stride] = (uint16_t)sb;
-                const Leaf l = leaf_of(EVOGP_LDG(typ + lf), EVOGP_LDG(val + lf), V);
+                const int lf = cx ? y : x;
+                const Leaf l = leaf_of(k.t[lf], bits_f32(k.v[lf]), V);
                 out[own] = cx ? leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), l, 0)
                               : leaf_instr(opcode(FM_VA, b), opcode(FM_KA, b), l, 0);
             }
         } else {
-            // IF(a, b, c): produce the three values in descending-need order (ties: c, b, a — the
-            // reference's order); the last produced sits in acc, the one before on the stack top.
-            int pos[3];
-            uint32_t inf[3];
-            pos[0] = i + 1;
-            inf[0] = SA[pos[0] * stride];
-            pos[1] = pos[0] + a_sz(inf[0]);
-            inf[1] = SA[pos[1] * stride];
-            pos[2] = pos[1] + a_sz(inf[1]);
-            inf[2] = SA[pos[2] * stride];
-            int nd[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) nd[k] = a_cplx(inf[k]) ? a_need(inf[k]) : 0;
-            int o0 = 2, o1 = 1, o2 = 0;   // c, b, a; stable bubble sort by need, descending
-            if (nd[o1] > nd[o0]) { const int s = o0; o0 = o1; o1 = s; }
-            if (nd[o2] > nd[o1]) { const int s = o1; o1 = o2; o2 = s; }
-            if (nd[o1] > nd[o0]) { const int s = o0; o0 = o1; o1 = s; }
-            int cur = st;
-            uint32_t perm = 0;   // 2 bits per operand a,b,c: 0 acc, 1 stack top, 2 stack top-1
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int k = j == 0 ? o0 : (j == 1 ? o1 : o2);
-                const uint32_t lv = j == 0 ? live : 1u;
-                const uint32_t hj = j == 0 ? height : height_in + (uint32_t)(j - 1);   // stack height when entity j starts
-                const uint32_t ik = k == 0 ? inf[0] : (k == 1 ? inf[1] : inf[2]);
-                const int pk = k == 0 ? pos[0] : (k == 1 ? pos[1] : pos[2]);
-                if (a_cplx(ik)) {
-                    SB[pk * stride] = (uint16_t)((uint32_t)cur | (lv << 11) | (hj << 12));
-                    cur += a_ni(ik);
-                } else {
-                    out[cur] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ + pk), EVOGP_LDG(val + pk), V),
-                                          lv ? ((hj + 1) << I_PUSH_SHIFT) : 0);
-                    cur += 1;
-                }
-                perm |= (uint32_t)(2 - j) << (2 * k);
-            }
-            // the first two produced values sit in slots height_in (older) and height_in + 1
+            // IF(a, b, c): the value produced last sits in acc, the one before in slot height_in + 1,
+            // the first in slot height_in
+            const int a = i + 1, b = a + k.s[a], c = b + k.s[b];
+            const uint32_t perm = (2u - (k.q[a] & 3)) | ((2u - (k.q[b] & 3)) << 2) | ((2u - (k.q[c] & 3)) << 4);
             out[own] = mk2((uint32_t)C_IF | (perm << I_IDXA_SHIFT) | (height_in << I_IDXB_SHIFT), 0);
+            my_max = my_max > (int)height_in + 2 ? my_max : (int)height_in + 2;
         }
     }
-    return root_need;
+    const int total = k.M[len];
+    if (ln.lane == 0 && total < Lp) out[total] = mk2(C_END, 0);
+    const int need = lanes_max(my_max);
+    if (need > depth_budget) {   // cannot happen for well-formed rows (stack_depth_bound); fail safe
+        lanes_sync();
+        emit_nan(ln, out, Lp);
+        return -1;
+    }
+    return need;
 }
-
 
 // Multi-output rows (out_len > 1).  The reference's multiOutput branch makes EVERY function
 // node hand its right-most child's value to its father (forward.cu:236-242: `top_val =
 // right_node` is unconditional), so a subtree's value is simply its right-most leaf — the last
 // node of its prefix span — and the only arithmetic with an effect is each OUT node applying its
 // function to those leaves and adding the result to outs[outIndex].  The program is therefore a
-// flat list of leaf-operand instructions, one per OUT node, emitted in the reference's
-// processing order (last node first) so the float sums into outs[] associate identically.
-// No operand stack.  Returns 0, or -1 for a malformed row.
-__host__ __device__ inline int lower_tree_multi(const float *val, const int16_t *typ, int len, int L, int Lp, int V,
-                                                int O, uint2 *out, uint32_t *SA, int stride) {
-    bool bad = len < 1 || len > L;
-    if (bad) len = 0;
-    int slot = 0;
-    for (int i = len - 1; i >= 0 && !bad; --i) {
-        const int t = EVOGP_LDG(typ + i);
-        const int ar = node_arity<true>(t);
-        if (ar == 0) {
-            SA[i * stride] = 1;
-            continue;
+// flat list of leaf-operand instructions, one group per OUT node, in the reference's processing
+// order (last node first) so the float sums into outs[] associate identically.  No operand stack.
+__host__ __device__ inline int lower_tree_multi(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
+                                                int len, int L, int Lp, int V, int O, uint2 *out, LowerScratch k,
+                                                bool have_sizes) {
+    if (!lower_stage<true>(ln, val, typ, size, len, L, k, have_sizes)) {
+        emit_nan(ln, out, Lp);
+        return -1;
+    }
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int t = k.t[i], ar = arity_of(t, true);
+        k.M[i] = (uint16_t)((ar != 0 && (t & NT_OUT)) ? (ar == 1 ? 1 : 2) : 0);
+    }
+    lanes_sync();
+    lanes_exclusive_scan(ln, k.M, len);
+    const int total = k.M[len];
+    if (total + 1 > Lp) {   // cannot happen: an OUT node's slots never exceed its own node count
+        emit_nan(ln, out, Lp);
+        return -1;
+    }
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int t = k.t[i], ar = arity_of(t, true);
+        if (ar == 0 || !(t & NT_OUT)) continue;
+        const int mine = ar == 1 ? 1 : 2;
+        int slot = total - (int)k.M[i] - mine;             // nodes are emitted last-first
+        int last[3] = {0, 0, 0}, c = i + 1;
+        for (int a = 0; a < ar; ++a) {
+            c += k.s[c];
+            last[a] = c - 1;                               // right-most leaf of child a
         }
-        int c = i + 1, sz = 1, last[3] = {0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (k < ar && !bad) {
-                if (c >= len) {
-                    bad = true;
-                } else {
-                    const int cs = (int)SA[c * stride];
-                    c += cs;
-                    sz += cs;
-                    last[k] = c - 1;   // right-most leaf of child k
-                }
-            }
-        }
-        if (bad) break;
-        SA[i * stride] = (uint32_t)sz;
-        if (!(t & NT_OUT)) continue;
-        const uint32_t bits = f32_bits(EVOGP_LDG(val + i));           // kernel.h:105-113
+        const uint32_t bits = k.v[i];                      // kernel.h:105-113
         const unsigned func = (unsigned)(int)(int16_t)(bits & 0xFFFF);
         const unsigned oi = (unsigned)(int)(int16_t)(bits >> 16);
         const uint32_t outbits = I_OUT | ((oi < (unsigned)O ? oi : I_IDXB_MASK) << I_IDXB_SHIFT);
-        if (slot + 2 > Lp) { bad = true; break; }                     // cannot happen: slots <= nodes
+        const Leaf la = leaf_of(k.t[last[0]], bits_f32(k.v[last[0]]), V);
         if (ar == 1) {
             const int u = unary_slot(func);
-            out[slot++] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u),
-                                     leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V), outbits);
+            out[slot] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u), la, outbits);
         } else if (ar == 2) {
             const int b = binary_slot(func);
-            out[slot++] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V), 0);
-            out[slot++] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b),
-                                     leaf_of(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V), outbits);
-        } else {
-            // C_IF3, two slots: {hdr, a} {b, c}; b/c words hold constant bits or a variable index
-            const Leaf la = leaf_of(EVOGP_LDG(typ + last[0]), EVOGP_LDG(val + last[0]), V);
-            const Leaf lb = leaf_of(EVOGP_LDG(typ + last[1]), EVOGP_LDG(val + last[1]), V);
-            const Leaf lc = leaf_of(EVOGP_LDG(typ + last[2]), EVOGP_LDG(val + last[2]), V);
+            out[slot] = leaf_instr(C_LOAD_V, C_LOAD_K, la, 0);
+            out[slot + 1] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), leaf_of(k.t[last[1]], bits_f32(k.v[last[1]]), V), outbits);
+        } else {   // C_IF3, two slots: {hdr, a} {b, c}; b/c words hold constant bits or a variable index
+            const Leaf lb = leaf_of(k.t[last[1]], bits_f32(k.v[last[1]]), V), lc = leaf_of(k.t[last[2]], bits_f32(k.v[last[2]]), V);
             const uint32_t hdr = (uint32_t)C_IF3 | outbits | (la.is_const ? I_IF3_ACONST : (la.bits << I_IDXA_SHIFT)) |
                                  (lb.is_const ? I_IF3_BCONST : 0u) | (lc.is_const ? I_IF3_CCONST : 0u);
-            out[slot++] = mk2(hdr, la.is_const ? la.bits : 0u);
-            out[slot++] = mk2(lb.bits, lc.bits);
+            out[slot] = mk2(hdr, la.is_const ? la.bits : 0u);
+            out[slot + 1] = mk2(lb.bits, lc.bits);
         }
     }
-    if (!bad && len > 0 && (int)SA[0] != len) bad = true;
-    if (bad || len == 0) {
-        out[0] = mk2(C_NAN, 0);
-        if (Lp > 1) out[1] = mk2(C_END, 0);
-        return -1;
-    }
-    if (slot < Lp) out[slot] = mk2(C_END, 0);
+    if (ln.lane == 0 && total < Lp) out[total] = mk2(C_END, 0);
     return 0;
 }
 
 template <bool MULTI>
-__host__ __device__ inline int lower_tree(const float *val, const int16_t *typ, int len, int L, int Lp, int V, int O,
-                                          int depth_budget, uint2 *out, uint32_t *SA, uint16_t *SB, int stride) {
-    if (MULTI) return lower_tree_multi(val, typ, len, L, Lp, V, O, out, SA, stride);
-    return lower_tree_single(val, typ, len, L, Lp, V, O, depth_budget, out, SA, SB, stride);
+__host__ __device__ inline int lower_tree(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
+                                          int L, int Lp, int V, int O, int depth_budget, uint2 *out, LowerScratch k,
+                                          bool have_sizes = true) {
+    if (MULTI) return lower_tree_multi(ln, val, typ, size, len, L, Lp, V, O, out, k, have_sizes);
+    return lower_tree_single(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes);
 }
 
 #ifdef __CUDACC__
 struct LowerArgs {
     const float *value;
     const int16_t *type;
-    const int16_t *size;   // tree lengths: size[n * len_stride]  (len_stride = L for a packed subtree_size array)
-    uint2 *prog;        // [P][Lp]
-    unsigned *sched;    // 64 scheduler words, zeroed here (the replay kernel runs after this one)
-    int P, L, Lp, V, O, depth_budget, len_stride;
+    const int16_t *size;      // packed subtree_size rows [P][L], or (rows_have_sizes == 0) one length per tree
+    uint2 *prog;              // [P][Lp]
+    unsigned *sched;          // 64 scheduler words, zeroed here (the replay kernel runs after this one)
+    int P, L, Lp, V, O, depth_budget, rows_have_sizes;
 };
 
-// Shared-memory plan of one CTA (T trees, row width L): SA u32 [L][T], SB u16 [L][T] — per-node scratch laid
-// out [node][thread], conflict-free for any mix of node indices.  Rows are read straight from global memory
-// (L2-resident): staging them in shared memory with cp.async was measured SLOWER (158 us vs 84 us at config 2)
-// because the extra 392 B/thread halves the resident warps of this latency-bound, divergent kernel.
-__host__ __device__ inline size_t lower_smem_bytes(int L, int T) { return (size_t)L * T * 6; }
-
+// one warp per tree, grid-stride over the population
 template <bool MULTI>
-__global__ void __launch_bounds__(128) lower_kernel(LowerArgs g) {
-    extern __shared__ __align__(16) uint32_t scratch[];
-    const int T = blockDim.x, tid = threadIdx.x;
-    uint32_t *SA = scratch;
-    uint16_t *SB = reinterpret_cast<uint16_t *>(SA + (size_t)g.L * T);
-    if (blockIdx.x == 0 && tid < 64) g.sched[tid] = 0;     // ticket counters of the replay kernel(s) that follow
-    const int n = blockIdx.x * T + tid;
-    if (n >= g.P) return;
-    const int len = g.size[(size_t)n * g.len_stride];
-    lower_tree<MULTI>(g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, len, g.L, g.Lp, g.V, g.O, g.depth_budget,
-                      g.prog + (size_t)n * g.Lp, SA + tid, SB + tid, T);
+__global__ void __launch_bounds__(256) lower_kernel(LowerArgs g) {
+    extern __shared__ __align__(16) unsigned char lower_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const size_t per_warp = (lower_scratch_bytes(g.L) + 15) & ~(size_t)15;
+    const LowerScratch k = carve_scratch(lower_smem + warp * per_warp, g.L);
+    if (blockIdx.x == 0 && threadIdx.x < 64) g.sched[threadIdx.x] = 0;     // ticket counters of the replay kernel
+    const Lanes ln{lane, 32};
+    for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
+        // rows_have_sizes == 0 (host path uploads one length per tree): sizes are recomputed from the arities
+        const int16_t *srow = g.rows_have_sizes ? g.size + (size_t)n * g.L : nullptr;
+        const int len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
+        lower_tree<MULTI>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
+                          g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0);
+        __syncwarp();
+    }
 }
 #endif
 

@@ -18,14 +18,14 @@ extern "C" float oracle_apply_binary(unsigned f, float a, float b);
 using namespace evogp;
 
 template <bool MULTI>
-static int run_row(const float *val, const int16_t *typ, int len, int L, int V, int O, const float *X, int N,
-                   float *out, int *need_out, int *ninstr_out, int *maxsp_out) {
+static int run_row(const float *val, const int16_t *typ, const int16_t *size, int len, int L, int V, int O, const float *X,
+                   int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out) {
     const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
-    std::vector<uint32_t> SA(L + 1);
-    std::vector<uint16_t> SB(L + 1);
+    std::vector<unsigned char> mem(lower_scratch_bytes(L) + 64);
+    const LowerScratch scratch = carve_scratch(mem.data(), L);
     const int budget = stack_depth_bound(L);
-    const int need = lower_tree<MULTI>(val, typ, len, L, Lp, V, O, budget, prog.data(), SA.data(), SB.data(), 1);
+    const int need = lower_tree<MULTI>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch);
     *need_out = need;
     int ninstr = 0;
     while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
@@ -120,7 +120,7 @@ static int run_row(const float *val, const int16_t *typ, int len, int L, int V, 
 
 extern "C" int harness_batch_forward(int P, int N, int L, int V, int O, const float *value, const int16_t *type,
                                      const int16_t *size, const float *X, float *out, int *need, int *ninstr,
-                                     int *maxsp) {
+                                     int *maxsp, int use_sizes) {
     // same floating-point environment as the oracle (and the GPU): flush-to-zero
     const unsigned saved_csr = _mm_getcsr();
     _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
@@ -129,9 +129,11 @@ extern "C" int harness_batch_forward(int P, int N, int L, int V, int O, const fl
     for (int n = 0; n < P; ++n) {
         const int len = size[(size_t)n * L];
         int rc;
-        if (O > 1) rc = run_row<true>(value + (size_t)n * L, type + (size_t)n * L, len, L, V, O, X, N,
+        // use_sizes: 1 = pass the subtree_size row (verified / trusted), 0 = pass none (recomputed from arities)
+        const int16_t *srow = use_sizes ? size + (size_t)n * L : nullptr;
+        if (O > 1) rc = run_row<true>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
                                       out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n);
-        else rc = run_row<false>(value + (size_t)n * L, type + (size_t)n * L, len, L, V, O, X, N,
+        else rc = run_row<false>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
                                  out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n);
         if (rc) return rc * 1000000 - n;
     }

@@ -59,7 +59,7 @@ def test_scalar_argument_errors_need_no_gpu(native):
     assert L.evogp_generate(4, 2000, 1, 1, 1, 0.5, 0.5, *([None] * 8)) == 1
     assert L.evogp_generate(4, 64, 1, 1, 1, 1.5, 0.5, *([None] * 8)) == 1 and b"out_prob" in L.evogp_last_error()
     assert L.evogp_SR_fitness(4, 5, 8, 2, 1, 1, None, None, None, None, None, None, 4, None, 0, None) == 3
-    assert L.evogp_eval_workspace_bytes(1000, 64) >= 1000 * 64 * 8
+    assert L.evogp_eval_workspace_bytes(1000, 64) >= 256      # scheduler words only: programs live in shared memory
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -26,7 +26,7 @@ def harness(orc):
     return C.CDLL(OUT)
 
 
-def run(harness, v, t, s, X, O):
+def run(harness, v, t, s, X, O, use_sizes=1):
     v = np.ascontiguousarray(v, np.float32); t = np.ascontiguousarray(t, np.int16); s = np.ascontiguousarray(s, np.int16)
     X = np.ascontiguousarray(X, np.float32)
     P, L = v.shape
@@ -34,7 +34,7 @@ def run(harness, v, t, s, X, O):
     out = np.zeros((P, N, O), np.float32)
     need = np.zeros(P, np.int32); ninstr = np.zeros(P, np.int32); maxsp = np.zeros(P, np.int32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = harness.harness_batch_forward(P, N, L, V, O, vp(v), vp(t), vp(s), vp(X), vp(out), vp(need), vp(ninstr), vp(maxsp))
+    rc = harness.harness_batch_forward(P, N, L, V, O, vp(v), vp(t), vp(s), vp(X), vp(out), vp(need), vp(ninstr), vp(maxsp), use_sizes)
     assert rc == 0, f"harness failed rc={rc}"
     return out, need, ninstr, maxsp
 
@@ -140,3 +140,22 @@ def test_malformed_rows_lower_to_nan(harness, orc):
     X, _ = make_data(3, 2)
     got, need, *_ = run(harness, v, t, s, X, 1)
     assert np.isnan(got[:4]).all() and (need[:4] == -1).all()
+
+
+def test_sizes_are_verified_not_trusted(harness, orc):
+    """The reference's evaluator reads only subtree_size[0] (forward.cu:283): rows whose interior sizes are
+    stale, or that come without a size row at all, must lower to the same program."""
+    v, t, s = make_forest(orc, 1500, 64, 3, 1, ARITH_FUNCS + ["if", "sin"], 4, keys=(31, 32), consts=(-1.0, 0.5))
+    X, _ = make_data(17, 3, seed=5)
+    want = orc.batch_forward(v, t, s, X, 1)
+    got_nosize, need0, *_ = run(harness, v, t, s, X, 1, use_sizes=0)
+    assert same(got_nosize, want)
+    rng = np.random.default_rng(0)
+    stale = s.copy()
+    rows = rng.integers(0, 1500, 600)
+    cols = (rng.integers(1, 64, 600) % np.maximum(s[rows, 0], 2)).clip(1)
+    stale[rows, cols] = rng.integers(0, 70, 600).astype(np.int16)        # corrupt interior entries, keep size[:,0]
+    got_stale, need1, *_ = run(harness, v, t, stale, X, 1)
+    assert same(got_stale, want)
+    got_ref, need2, *_ = run(harness, v, t, s, X, 1)
+    assert np.array_equal(need0, need2) and np.array_equal(need1, need2)
