@@ -41,6 +41,9 @@ struct ReplayArgs {
     int P, Lp, N, V, O;
     int NP;                 // N rounded up to a whole number of passes
     int npass, depth, mode;
+    // datapoint tiling (dataset larger than the shared-memory staging area): this launch covers datapoints
+    // [d_base, d_base + N) of N_total; loss modes carry the running sum in out[] between launches
+    int d_base, N_total, first_tile, last_tile;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
                 FOR_K {
                     const int d = pass_off + dp_index<K>(lane, k);
                     if (d < g.N) {
-                        float *dst = g.out + ((size_t)tree * g.N + d) * g.O;
+                        float *dst = g.out + ((size_t)tree * g.N_total + g.d_base + d) * g.O;
                         if constexpr (MULTI) {
                             for (int o = 0; o < g.O; ++o) dst[o] = outs[o * SLOT + lane_off + (K >= 4 ? (k >> 2) * 128 + (k & 3) : k * 32)];
                         } else {
@@ -373,7 +376,10 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
         if (g.mode <= MODE_ABS) {
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) err += __shfl_xor_sync(0xffffffffu, err, s);
-            if (lane == 0) g.out[tree] = err / (float)(unsigned)g.N;   // forward.cu:478
+            if (lane == 0) {
+                if (!g.first_tile) err += g.out[tree];                        // running sum of the earlier tiles
+                g.out[tree] = g.last_tile ? err / (float)(unsigned)g.N_total : err;   // forward.cu:478
+            }
         }
         __syncwarp();   // every lane is done with prog[buf] before lane 0 re-targets it
         buf ^= 1;
@@ -463,27 +469,48 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     a.NP = a.npass * SLOT;
     a.depth = depth > kRegSlots ? depth - kRegSlots : 1;   // slots 0/1 live in registers
     depth = a.depth;
-    const size_t data = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * a.NP * 4;
     auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
-    int warps = 8;
-    while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
-    const size_t smem = data + warps * per_warp();
-    if (smem > (size_t)g_max_smem) {
-        set_error("dataset of %d x %d floats (+ labels) does not fit the %d B shared-memory staging area", a.N, a.V, g_max_smem);
-        return EVOGP_ERR_UNSUPPORTED;
+    // the dataset slice a launch stages: all of it when it fits next to >= 4 warps, else whole passes of it
+    const size_t per_dp = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * 4;   // bytes per datapoint
+    const int N_total = a.N;
+    int tile = a.NP;                                                                         // datapoints per launch
+    if (per_dp && per_dp * tile + 4 * per_warp() > (size_t)g_max_smem) {
+        const size_t room = (size_t)g_max_smem > 4 * per_warp() ? (size_t)g_max_smem - 4 * per_warp() : 0;
+        tile = (int)(room / per_dp / SLOT) * SLOT;
+        if (tile < SLOT || (a.N + tile - 1) / tile > 64) {
+            set_error("%d inputs + %d labels per datapoint do not fit the %d B shared-memory staging area", a.V, a.O, g_max_smem);
+            return EVOGP_ERR_UNSUPPORTED;
+        }
     }
-    EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long want = ((long long)a.P + warps - 1) / warps;
-    int grid = (int)(want < (long long)per_sm * g_sm_count ? want : (long long)per_sm * g_sm_count);
-    if (grid < 1) grid = 1;
+    const float *X0 = a.X, *Y0 = a.labels;
+    unsigned *sched0 = a.sched;
     if (g_ev_replay_begin) cudaEventRecord(g_ev_replay_begin, st);
-    kern<<<grid, warps * 32, smem, st>>>(a);
+    for (int d0 = 0, t = 0; d0 < N_total; d0 += tile, ++t) {
+        a.N = N_total - d0 < tile ? N_total - d0 : tile;
+        a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
+        a.NP = a.npass * SLOT;
+        a.d_base = d0; a.N_total = N_total; a.first_tile = d0 == 0; a.last_tile = d0 + tile >= N_total;
+        if (!ROWWISE) a.X = X0 + (size_t)d0 * a.V;
+        if (Y0) a.labels = Y0 + (size_t)d0 * a.O;
+        a.sched = sched0 + t;                                  // one ticket counter per launch (64 zeroed by lower_kernel)
+        const size_t data = per_dp * a.NP;
+        int warps = 8;
+        while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
+        const size_t smem = data + warps * per_warp();
+        EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long want = ((long long)a.P + warps - 1) / warps;
+        int grid = (int)(want < (long long)per_sm * g_sm_count ? want : (long long)per_sm * g_sm_count);
+        if (grid < 1) grid = 1;
+        kern<<<grid, warps * 32, smem, st>>>(a);
+        count_launch();
+        const int rc = check_launch("replay_kernel");
+        if (rc) return rc;
+    }
     if (g_ev_replay_end) cudaEventRecord(g_ev_replay_end, st);
-    count_launch();
-    return check_launch("replay_kernel");
+    return EVOGP_OK;
 }
 
 template <bool MULTI>

@@ -198,6 +198,30 @@ def test_batch_forward(native, orc, O, N):
     assert G.same_bits(got, want)   # exact ops only; out nodes accumulate in the reference's order
 
 
+@pytest.mark.parametrize("pop,L,V,O,N,funcs,layers", [(600, 128, 13, 3, 4096, ALL_FUNCS, 4),      # configs[3] shape (Wine-like)
+                                                       (800, 64, 40, 1, 3000, ARITH_FUNCS, 6),     # wide single-output dataset
+                                                       (300, 64, 100, 2, 2500, EXACT_FUNCS, 4)])
+def test_datasets_larger_than_shared_memory_are_tiled(native, orc, ref, pop, L, V, O, N, funcs, layers):
+    """(V + O) * N * 4 bytes exceeds the staging area: the launcher walks the datapoints in tiles and carries the
+    running error sum between launches; batch_forward tiles write disjoint slices."""
+    v, t, s = make_forest(orc, pop, L, V, O, funcs, layers, keys=(17, 4), consts=(-1.0, 0.5, 2.0))
+    X, y = make_data(N, V, O, seed=6)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    for use_mse in (True, False):
+        got = G.abi_sr_fitness(native, dv, dt, ds, dX, dy, use_mse)
+        want = ref.sr_fitness(dv, dt, ds, dX, dy, use_mse, kernel_type=4)
+        torch.cuda.synchronize()
+        G.assert_close_fitness(got, want, rtol=RTOL, what=f"tiled fitness V={V} N={N}")
+    bf = G.abi_batch_forward(native, dv, dt, ds, dX, O)
+    torch.cuda.synchronize()
+    if funcs is EXACT_FUNCS:
+        assert G.same_bits(bf, orc.batch_forward(v, t, s, X, O, nthreads=8))
+    else:
+        sub = slice(0, 64)
+        want_bf = orc.batch_forward(v[sub], t[sub], s[sub], X, O, nthreads=8)
+        G.assert_close_fitness(bf[sub], want_bf, rtol=5e-3, atol=1e-5, what="tiled batch_forward")
+
+
 # --------------------------------------------------------------------------- edge cases
 def _chain_forest(L, kind):
     """Degenerate shapes: 'unary' = neg(neg(...x0)), 'left' = ((x0+x1)+x1)+..., 'right' = x0+(x1+(x1+...)),
