@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — tree-evals/s of the batched fitness evaluation (BASELINE.json metric).
 
-A step = one SR-fitness pass (lowering + replay kernels) over this rank's population shard
+A step = one SR-fitness pass (lower_kernel + replay_kernel) over this rank's population shard
 against the whole dataset, plus — for N > 1 — the single all-gather of fitness scalars.
 Workload at N = 1: BASELINE.json configs[1] (synthetic SR, 3 inputs, pop 100000, max_tree_len 64,
 1024 datapoints).  For N > 1 every rank holds a shard of that size (weak scaling; the population
@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if mask & bit:
                         self.reasons.add(k)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:   # NVML missing: report that rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -248,9 +248,12 @@ def run_ours(args):
                         "path": "evogp_SR_fitness_host (C ABI, pinned host buffers, chunked copy/compute overlap)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "replay_kernel<8,false,false>", "achieved": ach, "peak": peak,
-                             "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": ach / peak,
+                             "traffic": 52.9e6,   # dram read+write per launch, profiles/r1_final_ncu.txt
+                             "traffic_source": "ncu --set full, profiles/r1_final_ncu.txt (same workload shard)",
+                             "algorithmic_bytes": algorithmic_bytes(hi - lo, L, N, V, O), "peak_source": peak_src,
                              "kernel_ms": kms, "kernel_share_of_step": kms / float(np.mean(step_ms)),
-                             "note": "interpreter kernel: bound by instruction issue, not HBM (DESIGN.md)"},
+                             "note": "interpreter kernel: bound by instruction issue (65 %) and the shared-memory pipe (76 %), not HBM (DESIGN.md)"},
                 "clocks": clocks, "wall_s_timed_region": t_wall, "fitness_mean_check": fit_host_check}
         if world == 1 and not args.no_cpu:
             v, ms, threads, sample = cpu_reference_leg(3, 1, target_seconds=10.0)
@@ -280,8 +283,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's CUDA kernels")
