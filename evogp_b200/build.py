@@ -16,8 +16,8 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB_SO = os.path.join(LIBDIR, "libevogp_b200.so")
 OPS_SO = os.path.join(LIBDIR, "evogp_cuda_ops.so")
 
-CU_SOURCES = ["runtime.cu", "eval.cu", "splice.cu", "generate.cu", "host_api.cu"]
-CU_HEADERS = ["common.cuh", "program.cuh", "lower.cuh", "fastpath_k8.inc", "../../include/evogp_b200.h"]
+CU_SOURCES = ["runtime.cu", "eval.cu", "splice.cu", "generate.cu", "nextgen.cu", "host_api.cu"]
+CU_HEADERS = ["common.cuh", "program.cuh", "lower.cuh", "fastpath_k8.inc", "gen_tree.cuh", "../../include/evogp_b200.h"]
 
 # -use_fast_math: the reference's numeric contract (its setup.py passes the same flag), see DESIGN.md
 NVCC_FLAGS = ["-O3", "-std=c++17", "-use_fast_math", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

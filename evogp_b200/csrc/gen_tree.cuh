@@ -1,0 +1,109 @@
+// gen_tree.cuh — per-tree random generation shared by generate.cu and nextgen.cu.
+// Bit-identical to the reference's treeGPGenerate draw sequence (src/evogp/cuda/generate.cu:16-173):
+// FNV-1a seed (kernel.h:157-180), thrust taus88, same draw order, downward roulette scan.
+#pragma once
+#include "common.cuh"
+
+namespace evogp {
+
+// kernel.h:160-172: low 32 bits of 64-bit FNV-1a over the bytes of {n, k1, k2}
+__device__ __forceinline__ uint32_t tree_seed(uint32_t n, uint32_t k1, uint32_t k2) {
+    uint64_t h = 14695981039346656037ULL;
+    const uint32_t a[3] = {n, k1, k2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            h ^= (uint64_t)((a[i] >> (8 * b)) & 0xFFu);
+            h *= 1099511628211ULL;
+        }
+    return (uint32_t)h;
+}
+
+// thrust::random::taus88 (kernel.h:20): three LFSRs, all seeded with the same word
+struct Taus88 {
+    uint32_t z1, z2, z3;
+    __device__ __forceinline__ explicit Taus88(uint32_t s) : z1(s), z2(s), z3(s) {}
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t b;
+        b = ((z1 << 13) ^ z1) >> 19;
+        z1 = ((z1 & 0xFFFFFFFEu) << 12) ^ b;
+        b = ((z2 << 2) ^ z2) >> 25;
+        z2 = ((z2 & 0xFFFFFFF8u) << 4) ^ b;
+        b = ((z3 << 3) ^ z3) >> 11;
+        z3 = ((z3 & 0xFFFFFFF0u) << 17) ^ b;
+        return z1 ^ z2 ^ z3;
+    }
+    // thrust::uniform_real_distribution<float>(0,1): float(u32) / 2^32 (exact scaling; can return 1.0f)
+    __device__ __forceinline__ float uniform() { return __uint2float_rn(next()) * 2.3283064365386963e-10f; }
+};
+
+
+struct GrowParams {
+    const float *leaf;     // [10]  depth -> leaf probability   (shared or global memory)
+    const float *roul;     // [29]  cumulative function roulette
+    const float *consts;   // [S]   global memory
+    unsigned L, V, O, S;
+    float outProb, constProb;
+};
+
+// Grows one tree into val[] (value bits) and ts[] (type | size << 16); returns the node count.
+// The frame stack is a register: frames have strictly increasing depth, so "children still owed at depth d"
+// is a 4-bit field of one 64-bit word.  Subtree sizes need no stack: scanning the prefix backwards,
+// size[i] = 1 + size[c1] + size[c2] + ... with c1 = i + 1, c2 = c1 + size[c1].
+template <bool MULTI>
+__device__ inline int grow_tree(Taus88 &rng, const GrowParams &g, uint32_t *val, uint32_t *ts) {
+    uint64_t owed = 1;   // root frame {1, 0}
+    int d = 0, cnt = 0;
+    while (d >= 0 && cnt < (int)g.L) {
+        owed -= 1ull << (4 * d);                                   // cd.childs-- (generate.cu:61)
+        const float leafp = d < kMaxFullDepth ? g.leaf[d] : 2.0f;  // reference indexes out of bounds at d >= 10
+        uint32_t vbits;
+        int type, arity = 0;
+        if (rng.uniform() >= leafp) {                              // function node (:71)
+            const float r = rng.uniform();
+            int k = 0;
+            for (int i = F_END - 1; i >= 0; --i)                   // downward roulette scan (:74-84)
+                if (r >= g.roul[i]) { k = i + 1; break; }
+            type = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
+            arity = type - 1;
+            vbits = __float_as_uint((float)k);
+            if (MULTI) {
+                if (rng.uniform() <= g.outProb) {                  // output node (:88-96)
+                    const uint32_t oi = rng.next() % g.O;
+                    vbits = ((uint32_t)k & 0xFFFFu) | (oi << 16);  // kernel.h:105-113
+                    type += NT_OUT;
+                }
+            }
+        } else if (rng.uniform() <= g.constProb) {                 // constant leaf (:109-114)
+            vbits = __float_as_uint(__ldg(g.consts + rng.next() % g.S));
+            type = NT_CONST;
+        } else {                                                   // variable leaf (:116-120)
+            vbits = __float_as_uint((float)(rng.next() % g.V));
+            type = NT_VAR;
+        }
+        val[cnt] = vbits;
+        ts[cnt] = (uint32_t)type & 0xFFFFu;
+        ++cnt;
+        if (arity > 0 && d + 1 < 16) {
+            ++d;
+            owed |= (uint64_t)arity << (4 * d);
+        } else {
+            while (d >= 0 && ((owed >> (4 * d)) & 0xF) == 0) --d;
+        }
+    }
+    for (int i = cnt - 1; i >= 0; --i) {                           // subtree sizes, leaves -> root (:130-158)
+        const int t = ts[i] & NT_MASK;
+        const int ar = t <= NT_CONST ? 0 : t - 1;
+        int sz = 1, c = i + 1;
+        for (int k = 0; k < ar; ++k) {
+            const int cs = c < cnt ? (int)(ts[c] >> 16) : 0;
+            sz += cs;
+            c += cs;
+        }
+        ts[i] |= (uint32_t)sz << 16;
+    }
+    return cnt;
+}
+
+}  // namespace evogp

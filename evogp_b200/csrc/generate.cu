@@ -15,41 +15,9 @@
 //   * subtree sizes need no stack either: scanning the prefix backwards,
 //     size[i] = 1 + size[c1] + size[c2] + ... with c1 = i+1, c2 = c1 + size[c1];
 //   * rows leave the SM through warp-cooperative, coalesced, zero-filled stores.
-#include "common.cuh"
+#include "gen_tree.cuh"
 
 namespace evogp {
-
-// kernel.h:160-172: low 32 bits of 64-bit FNV-1a over the bytes of {n, k1, k2}
-__device__ __forceinline__ uint32_t tree_seed(uint32_t n, uint32_t k1, uint32_t k2) {
-    uint64_t h = 14695981039346656037ULL;
-    const uint32_t a[3] = {n, k1, k2};
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            h ^= (uint64_t)((a[i] >> (8 * b)) & 0xFFu);
-            h *= 1099511628211ULL;
-        }
-    return (uint32_t)h;
-}
-
-// thrust::random::taus88 (kernel.h:20): three LFSRs, all seeded with the same word
-struct Taus88 {
-    uint32_t z1, z2, z3;
-    __device__ __forceinline__ explicit Taus88(uint32_t s) : z1(s), z2(s), z3(s) {}
-    __device__ __forceinline__ uint32_t next() {
-        uint32_t b;
-        b = ((z1 << 13) ^ z1) >> 19;
-        z1 = ((z1 & 0xFFFFFFFEu) << 12) ^ b;
-        b = ((z2 << 2) ^ z2) >> 25;
-        z2 = ((z2 & 0xFFFFFFF8u) << 4) ^ b;
-        b = ((z3 << 3) ^ z3) >> 11;
-        z3 = ((z3 & 0xFFFFFFF0u) << 17) ^ b;
-        return z1 ^ z2 ^ z3;
-    }
-    // thrust::uniform_real_distribution<float>(0,1): float(u32) / 2^32 (exact scaling; can return 1.0f)
-    __device__ __forceinline__ float uniform() { return __uint2float_rn(next()) * 2.3283064365386963e-10f; }
-};
 
 struct GenArgs {
     const unsigned *keys;
@@ -83,57 +51,10 @@ __global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
         uint32_t *val = s_val + (size_t)threadIdx.x * pitch;
         uint32_t *ts = s_ts + (size_t)threadIdx.x * pitch;
         Taus88 rng(tree_seed(n, g.keys[0], g.keys[1]));
-        uint64_t owed = 1;   // 4 bits per depth: children still to generate; root frame {1, 0}
-        int d = 0, cnt = 0;
-        while (d >= 0 && cnt < (int)g.L) {
-            owed -= 1ull << (4 * d);                                   // cd.childs-- (generate.cu:61)
-            const float leafp = d < kMaxFullDepth ? s_leaf[d] : 2.0f;  // reference indexes out of bounds at d >= 10
-            uint32_t vbits;
-            int type, arity = 0;
-            if (rng.uniform() >= leafp) {                              // function node (:71)
-                const float r = rng.uniform();
-                int k = 0;
-                for (int i = F_END - 1; i >= 0; --i)                   // downward roulette scan (:74-84)
-                    if (r >= s_roul[i]) { k = i + 1; break; }
-                type = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
-                arity = type - 1;
-                vbits = __float_as_uint((float)k);
-                if (MULTI) {
-                    if (rng.uniform() <= g.outProb) {                  // output node (:88-96)
-                        const uint32_t oi = rng.next() % g.O;
-                        vbits = ((uint32_t)k & 0xFFFFu) | (oi << 16);  // kernel.h:105-113
-                        type += NT_OUT;
-                    }
-                }
-            } else if (rng.uniform() <= g.constProb) {                 // constant leaf (:109-114)
-                vbits = __float_as_uint(__ldg(g.consts + rng.next() % g.S));
-                type = NT_CONST;
-            } else {                                                   // variable leaf (:116-120)
-                vbits = __float_as_uint((float)(rng.next() % g.V));
-                type = NT_VAR;
-            }
-            val[cnt] = vbits;
-            ts[cnt] = (uint32_t)type & 0xFFFFu;
-            ++cnt;
-            if (arity > 0 && d + 1 < 16) {
-                ++d;
-                owed |= (uint64_t)arity << (4 * d);
-            } else {
-                while (d >= 0 && ((owed >> (4 * d)) & 0xF) == 0) --d;
-            }
-        }
-        // subtree sizes, leaves -> root (:130-158), stack-free
-        for (int i = cnt - 1; i >= 0; --i) {
-            const int t = ts[i] & NT_MASK;
-            const int ar = t <= NT_CONST ? 0 : t - 1;
-            int sz = 1, c = i + 1;
-            for (int k = 0; k < ar; ++k) {
-                const int cs = c < cnt ? (int)(ts[c] >> 16) : 0;
-                sz += cs;
-                c += cs;
-            }
-            ts[i] |= (uint32_t)sz << 16;
-        }
+        GrowParams gp;
+        gp.leaf = s_leaf; gp.roul = s_roul; gp.consts = g.consts;
+        gp.L = g.L; gp.V = g.V; gp.O = g.O; gp.S = g.S; gp.outProb = g.outProb; gp.constProb = g.constProb;
+        const int cnt = grow_tree<MULTI>(rng, gp, val, ts);
         len = cnt > 0 ? (int)(ts[0] >> 16) : 0;
         if (cnt < pitch) ts[cnt] = 0;
         // remember the valid length in the padding word of the row (pitch > L always)

@@ -1,0 +1,208 @@
+// nextgen.cu — one kernel for a whole generation step over the packed arrays:
+//     next[n] = current[order[n]]                                   n <  elite   (elitism)
+//     next[n] = mutate?(crossover(survivor a, survivor b))          n >= elite
+// This is the "next" row f-1 of SURVEY.md §8: in the reference (and in this repo's
+// reference-equivalent path, evogp_b200/algorithm/*.py) a generation is ~14 torch calls around three
+// kernels — gather the survivors (algorithm/crossover/default.py:37), draw indices and positions,
+// crossover, draw a mutation mask on the CPU, gather the mutants, generate donors, mutate, scatter
+// back, concatenate the elites (genetic_programming.py:110-118): ~1.0 ms of glue around 0.15 ms of
+// kernels at pop 100000.  Here the survivors are addressed through `order` (no gather), parents and
+// positions come from a counter-based generator (Philox4x32-10 keyed by the generation's keys and
+// the child index), the child is spliced in shared memory, the donor of a mutation is grown in
+// place by the same taus88 routine evogp_generate uses, and the row is written once.
+//
+// The operators are the reference's (mutation.cu:5-115 splice rules and fallbacks, generate.cu grow
+// method, selection/default.py truncation + elitism); the RANDOM STREAM is not (torch's generators
+// cannot be reproduced inside a kernel), so this path is statistically — not bit-for-bit —
+// equivalent to DefaultSelection/DefaultCrossover/DefaultMutation.  It is deterministic in
+// (keys, inputs), which is what replicated multi-GPU populations need.
+#include "gen_tree.cuh"
+
+namespace evogp {
+
+// Philox4x32-10 (Salmon et al., SC'11), counter = (n, stream, 0, 0), key = (k0, k1)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+struct NextGenArgs {
+    const float *value;      // current population [P][L]
+    const int16_t *type;
+    const int16_t *size;
+    const long long *order;  // [P] row indices, best first
+    const unsigned *keys;    // [2]
+    const float *depth2leaf, *roulette, *consts;
+    float *ovalue;
+    int16_t *otype;
+    int16_t *osize;
+    int P, L, elite, survivors;
+    unsigned V, O, S;
+    float mutationRate, outProb, constProb;
+};
+
+// source of output slot j of a splice (see splice.cu): recipient prefix / donor subtree / shifted tail
+struct SplicePlan {
+    int pos, dpos, dsub, diff, newlen;
+};
+__device__ __forceinline__ SplicePlan plan_splice(int rlen, int pos, int rsub, int dpos, int dsub, int L, bool ok) {
+    SplicePlan s;
+    ok = ok && dsub >= 1 && rlen + dsub - rsub <= L;        // mutation.cu:163, :279: too long -> keep the recipient
+    s.pos = ok ? pos : rlen;
+    s.dpos = dpos;
+    s.dsub = ok ? dsub : 0;
+    s.diff = ok ? dsub - rsub : 0;
+    s.newlen = rlen + s.diff;
+    return s;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256) nextgen_kernel(NextGenArgs g) {
+    extern __shared__ __align__(16) uint32_t ng_smem[];
+    __shared__ float s_leaf[kMaxFullDepth];
+    __shared__ float s_roul[F_END];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int L = g.L;
+    if (threadIdx.x < kMaxFullDepth) s_leaf[threadIdx.x] = g.depth2leaf[threadIdx.x];
+    if (threadIdx.x < F_END) s_roul[threadIdx.x] = g.roulette[threadIdx.x];
+    __syncthreads();
+    // per warp: child row (value bits, type|size<<16) and donor row, L words each
+    uint32_t *cv = ng_smem + (size_t)warp * 4 * L, *cts = cv + L, *dv = cts + L, *dts = dv + L;
+    const uint32_t k0 = g.keys[0], k1 = g.keys[1];
+
+    for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
+        float *ov = g.ovalue + (size_t)n * L;
+        int16_t *ot = g.otype + (size_t)n * L;
+        int16_t *os = g.osize + (size_t)n * L;
+        if (n < g.elite) {   // elitism: verbatim copy of the n-th best row
+            const size_t src = (size_t)g.order[n] * L;
+            for (int j = lane; j < L; j += 32) {
+                ov[j] = g.value[src + j];
+                ot[j] = g.type[src + j];
+                os[j] = g.size[src + j];
+            }
+            continue;
+        }
+        // ---- draws (warp-uniform: every lane computes the same Philox block) ----
+        const uint4 r0 = philox4x32_10((uint32_t)n, 0u, k0, k1), r1 = philox4x32_10((uint32_t)n, 1u, k0, k1);
+        const size_t lrow = (size_t)g.order[r0.x % (uint32_t)g.survivors] * L;
+        const size_t rrow = (size_t)g.order[r0.y % (uint32_t)g.survivors] * L;
+        const int llen = g.size[lrow], rlen = g.size[rrow];
+        const int lpos = (int)(r0.z % (uint32_t)max(llen, 1)), rpos = (int)(r0.w % (uint32_t)max(rlen, 1));
+        const bool rows_ok = llen >= 1 && llen <= L && rlen >= 1 && rlen <= L;
+        const SplicePlan cx = plan_splice(llen, lpos, rows_ok ? g.size[lrow + lpos] : 0, rpos,
+                                          rows_ok ? g.size[rrow + rpos] : 0, L, rows_ok);
+        // ---- crossover into shared memory ----
+        for (int j = lane; j < L; j += 32) {
+            uint32_t v = 0, ts = 0;
+            if (j < cx.newlen) {
+                size_t q;
+                int add = 0;
+                if (j < cx.pos) {
+                    q = lrow + j;
+                    if (j + g.size[q] > cx.pos) add = cx.diff;     // ancestor of the splice point
+                } else if (j < cx.pos + cx.dsub) q = rrow + cx.dpos + j - cx.pos;
+                else q = lrow + j - cx.diff;
+                v = __float_as_uint(g.value[q]);
+                ts = ((uint32_t)(uint16_t)g.type[q]) | ((uint32_t)(uint16_t)(g.size[q] + add) << 16);
+            }
+            cv[j] = v;
+            cts[j] = ts;
+        }
+        __syncwarp();
+        // ---- mutation: with probability mutationRate replace a random subtree by a freshly grown one ----
+        const float u = __uint2float_rn(r1.x) * 2.3283064365386963e-10f;
+        SplicePlan mu = plan_splice(cx.newlen, cx.newlen, 0, 0, 0, L, false);      // identity
+        if (u < g.mutationRate) {
+            int dlen = 0;
+            if (lane == 0) {
+                Taus88 rng(tree_seed((uint32_t)n, k0 ^ 0x5bd1e995u, k1));
+                GrowParams gp;
+                gp.leaf = s_leaf; gp.roul = s_roul; gp.consts = g.consts;
+                gp.L = (unsigned)L; gp.V = g.V; gp.O = g.O; gp.S = g.S; gp.outProb = g.outProb; gp.constProb = g.constProb;
+                const int cnt = grow_tree<MULTI>(rng, gp, dv, dts);
+                dlen = cnt > 0 ? (int)(dts[0] >> 16) : 0;
+            }
+            dlen = __shfl_sync(0xffffffffu, dlen, 0);
+            const int mpos = (int)(r1.y % (uint32_t)max(cx.newlen, 1));
+            mu = plan_splice(cx.newlen, mpos, (int)(cts[mpos] >> 16), 0, dlen, L, dlen >= 1);
+            __syncwarp();   // the donor row written by lane 0 is visible to every lane
+        }
+        // ---- final row: child (or mutated child) -> global, zero-filled tail ----
+        for (int j = lane; j < L; j += 32) {
+            uint32_t v = 0, t = 0, s = 0;
+            if (j < mu.newlen) {
+                if (j < mu.pos) {
+                    v = cv[j]; t = cts[j] & 0xFFFFu; s = cts[j] >> 16;
+                    if (j + (int)s > mu.pos) s += mu.diff;
+                } else if (j < mu.pos + mu.dsub) {
+                    const int q = j - mu.pos;
+                    v = dv[q]; t = dts[q] & 0xFFFFu; s = dts[q] >> 16;
+                } else {
+                    const int q = j - mu.diff;
+                    v = cv[q]; t = cts[q] & 0xFFFFu; s = cts[q] >> 16;
+                }
+            }
+            ov[j] = __uint_as_float(v);
+            ot[j] = (int16_t)t;
+            os[j] = (int16_t)s;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace evogp
+
+using namespace evogp;
+
+extern "C" int evogp_next_generation(int popSize, int gpLen, const float *value, const int16_t *type, const int16_t *subtree_size,
+                                     const long long *order, int eliteCnt, int survivorCnt, float mutationRate,
+                                     unsigned varLen, unsigned outLen, unsigned constSamplesLen, float outProb,
+                                     float constProb, const float *depth2leafProbs, const float *rouletteFuncs,
+                                     const float *constSamples, const unsigned *keys, float *value_res,
+                                     int16_t *type_res, int16_t *subtree_size_res, void *stream) {
+    EVOGP_REQUIRE(popSize > 0, "pop_size must be larger than 0, got %d", popSize);
+    EVOGP_REQUIRE(gpLen > 0 && gpLen <= kMaxStack, "gp_len must be in (0, %d], got %d", kMaxStack, gpLen);
+    EVOGP_REQUIRE(eliteCnt >= 0 && eliteCnt <= popSize, "elite_cnt must be in [0, pop_size], got %d", eliteCnt);
+    EVOGP_REQUIRE(survivorCnt > 0 && survivorCnt <= popSize, "survivor_cnt must be in (0, pop_size], got %d", survivorCnt);
+    EVOGP_REQUIRE(mutationRate >= 0.f && mutationRate <= 1.f, "mutation_rate must be in [0, 1], got %f", mutationRate);
+    EVOGP_REQUIRE(varLen > 0 && outLen > 0 && constSamplesLen > 0, "var_len, out_len, const_samples_len must be positive");
+    EVOGP_REQUIRE(outProb >= 0.f && outProb <= 1.f && constProb >= 0.f && constProb <= 1.f, "probabilities must be in [0, 1]");
+    int rc = ensure_device_ok();
+    if (rc) return rc;
+    NextGenArgs a;
+    a.value = value; a.type = type; a.size = subtree_size; a.order = order; a.keys = keys;
+    a.depth2leaf = depth2leafProbs; a.roulette = rouletteFuncs; a.consts = constSamples;
+    a.ovalue = value_res; a.otype = type_res; a.osize = subtree_size_res;
+    a.P = popSize; a.L = gpLen; a.elite = eliteCnt; a.survivors = survivorCnt;
+    a.V = varLen; a.O = outLen; a.S = constSamplesLen;
+    a.mutationRate = mutationRate; a.outProb = outProb; a.constProb = constProb;
+    const size_t per_warp = (size_t)gpLen * 16;
+    int warps = 8;
+    while (warps > 1 && warps * per_warp > 160 * 1024) warps >>= 1;
+    const size_t smem = warps * per_warp;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = ((long long)popSize + warps - 1) / warps;
+    const long long cap = (long long)sms * 8;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (outLen > 1) {
+        if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(nextgen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nextgen_kernel<true><<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(nextgen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nextgen_kernel<false><<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    }
+    count_launch();
+    return check_launch("next_generation");
+}

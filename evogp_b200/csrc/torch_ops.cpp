@@ -181,6 +181,32 @@ Tensor tree_batch_forward(int64_t pop_size, int64_t data_points, int64_t gp_len,
     return results;
 }
 
+Tensor3 tree_next_generation(int64_t pop_size, int64_t gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor order,
+                             int64_t elite_cnt, int64_t survivor_cnt, double mutation_rate, int64_t var_len, int64_t out_len,
+                             double out_prob, double const_prob, Tensor depth2leaf_probs, Tensor roulette_funcs,
+                             Tensor const_samples, Tensor keys) {
+    check_forest_args(pop_size, gp_len, var_len, out_len, value, node_type, subtree_size);
+    check_tensor(order, {pop_size}, at::kLong, "order");
+    check_tensor(keys, {2}, at::kUInt32, "keys");
+    check_tensor(depth2leaf_probs, {EVOGP_MAX_FULL_DEPTH}, at::kFloat, "depth2leaf_probs");
+    check_tensor(roulette_funcs, {EVOGP_FUNC_END}, at::kFloat, "roulette_funcs");
+    TORCH_CHECK(const_samples.is_cuda() && const_samples.is_contiguous() && const_samples.dim() == 1 &&
+                    const_samples.scalar_type() == at::kFloat && const_samples.numel() > 0,
+                "const_samples must be a non-empty contiguous 1-D float CUDA tensor");
+    c10::cuda::CUDAGuard guard(value.device());
+    auto out = alloc_forest(pop_size, gp_len, value);
+    check_rc(evogp_next_generation((int)pop_size, (int)gp_len, value.data_ptr<float>(), node_type.data_ptr<int16_t>(),
+                                   subtree_size.data_ptr<int16_t>(), reinterpret_cast<const long long *>(order.data_ptr<int64_t>()),
+                                   (int)elite_cnt, (int)survivor_cnt, (float)mutation_rate, (unsigned)var_len,
+                                   (unsigned)out_len, (unsigned)const_samples.numel(), (float)out_prob, (float)const_prob,
+                                   depth2leaf_probs.data_ptr<float>(), roulette_funcs.data_ptr<float>(),
+                                   const_samples.data_ptr<float>(), static_cast<const unsigned *>(keys.data_ptr()),
+                                   std::get<0>(out).data_ptr<float>(), std::get<1>(out).data_ptr<int16_t>(),
+                                   std::get<2>(out).data_ptr<int16_t>(), cur_stream(value)),
+             "tree_next_generation");
+    return out;
+}
+
 }  // namespace
 
 TORCH_LIBRARY(evogp_cuda, m) {
@@ -189,6 +215,7 @@ TORCH_LIBRARY(evogp_cuda, m) {
     m.def("tree_crossover(int pop_size_ori, int pop_size_new, int gp_len, Tensor value_ori, Tensor type_ori, Tensor subtree_size_ori, Tensor left_idx, Tensor right_idx, Tensor left_node_idx, Tensor right_node_idx) -> (Tensor, Tensor, Tensor)");
     m.def("tree_evaluate(int pop_size, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
     m.def("tree_SR_fitness(int pop_size, int data_points, int gp_len, int var_len, int out_len, bool useMSE, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor labels, int kernel_type) -> Tensor");
+    m.def("tree_next_generation(int pop_size, int gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor order, int elite_cnt, int survivor_cnt, float mutation_rate, int var_len, int out_len, float out_prob, float const_prob, Tensor depth2leaf_probs, Tensor roulette_funcs, Tensor const_samples, Tensor keys) -> (Tensor, Tensor, Tensor)");
     m.def("tree_batch_forward(int pop_size, int data_points, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
 }
 
@@ -199,4 +226,5 @@ TORCH_LIBRARY_IMPL(evogp_cuda, CUDA, m) {
     m.impl("tree_evaluate", &tree_evaluate);
     m.impl("tree_SR_fitness", &tree_SR_fitness);
     m.impl("tree_batch_forward", &tree_batch_forward);
+    m.impl("tree_next_generation", &tree_next_generation);
 }

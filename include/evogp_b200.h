@@ -103,6 +103,23 @@ int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, u
                         const float *variables, float *results, void *workspace, size_t workspace_bytes,
                         void *stream);
 
+/* One whole generation step in one kernel ("next" row f-1; no counterpart in the reference's kernel.h — it fuses
+ * what algorithm/genetic_programming.py:110-118, crossover/default.py and mutation/default.py do with ~14 torch
+ * calls around three kernels):
+ *   next[n] = current[order[n]]                                                      n <  eliteCnt
+ *   next[n] = mutate?( crossover(current[order[a]], current[order[b]]) ),  a, b < survivorCnt, otherwise
+ * order: int64[popSize] row indices, best first (torch.sort of the fitness).  Parents, splice positions and the
+ * mutation coin come from Philox4x32-10 keyed by keys[2] and the child index; mutation donors are grown in the
+ * kernel by the generator of evogp_generate (descriptor arguments as there).  Splice rules and fallbacks are the
+ * reference's; the random stream is not torch's, so results are deterministic in (keys, inputs) but not
+ * bit-comparable with the unfused operator sequence. */
+int evogp_next_generation(int popSize, int gpLen, const float *value, const int16_t *type, const int16_t *subtree_size,
+                          const long long *order, int eliteCnt, int survivorCnt, float mutationRate, unsigned varLen,
+                          unsigned outLen, unsigned constSamplesLen, float outProb, float constProb,
+                          const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
+                          const unsigned *keys, float *value_res, int16_t *type_res, int16_t *subtree_size_res,
+                          void *stream);
+
 /* Host-buffer form of evogp_SR_fitness: every pointer is HOST memory (pinned memory
  * makes the copies asynchronous).  Uploads the forest in row chunks on two streams so
  * H2D overlaps evaluation, downloads fitnesses[popSize], and returns after the result

@@ -219,3 +219,56 @@ def test_host_buffer_entry_point_matches_device_path(native, api):
     rc = native.abi().evogp_SR_fitness_host(30000, 1024, 64, 3, 1, 1, vp(hv.clone()), vp(ht), vp(hs), vp(hX), vp(hy), vp(out2), torch.cuda.current_device())
     assert rc == 0 and G.same_bits(out2, dev_fit.numpy())
     native.abi().evogp_host_release()
+
+
+def test_fused_generation_step(api, orc):
+    """tree_next_generation: structure, elitism, provenance, mutation share, determinism."""
+    tree, algorithm, problem, _ = api
+    torch.manual_seed(4)
+    P, L = 20000, 64
+    d = tree.GenerateDescriptor(max_tree_len=L, input_len=3, output_len=1, using_funcs=["+", "-", "*", "/"], max_layer_cnt=6,
+                                const_samples=[-1, 0, 1])
+    md = d.update(max_layer_cnt=3, const_samples=[7.5, 8.5])        # donor constants are recognisable
+    f0 = tree.Forest.random_generate(P, d)
+    fit = torch.rand(P, device="cuda")
+    fit[5] = float("nan")
+    keys = torch.tensor([11, 22], dtype=torch.uint32, device="cuda")
+    gp = algorithm.FusedGeneticProgramming(f0, md, mutation_rate=0.25, survival_rate=0.3, elite_rate=0.01)
+    f1 = gp.step(fit, keys)
+    v1, t1, s1 = host(f1)
+    orc.check_forest(v1, t1, s1, input_len=3)
+    v0, t0, s0 = host(f0)
+    order = torch.sort(torch.nan_to_num(fit, nan=float("-inf")), descending=True, stable=True).indices.cpu().numpy()
+    E, S = gp.elite_cnt, gp.survivor_cnt
+    assert E == 200 and S == 6000
+    assert np.array_equal(v1[:E].view(np.uint32), v0[order[:E]].view(np.uint32)) and np.array_equal(s1[:E], s0[order[:E]])
+    # tails are zero
+    cols = np.arange(L)[None, :]
+    assert not (v1[cols >= s1[:, :1]].any() or t1[cols >= s1[:, :1]].any())
+    # mutation share: donors carry constants 7.5 / 8.5 that no original tree has
+    has_donor = ((v1 == 7.5) | (v1 == 8.5)).any(axis=1)[E:]
+    frac = has_donor.mean()
+    assert 0.10 < frac < 0.25, frac      # 25 % mutate; a donor shows a constant ~2/3 of the time
+    # provenance: an unmutated child's root node comes from a survivor row, or (position 0) from the donor parent's subtree
+    surv_roots = set(map(tuple, np.stack([v0[order[:S], 0].view(np.uint32), t0[order[:S], 0].astype(np.uint32)], 1)))
+    kids = np.nonzero(~has_donor)[0][:2000] + E
+    all_nodes = set(zip(v0[order[:S]].view(np.uint32).ravel().tolist(), t0[order[:S]].astype(np.uint32).ravel().tolist()))
+    assert all((int(v1[k, 0].view(np.uint32)), int(t1[k, 0])) in all_nodes for k in kids)
+    # determinism in (keys, inputs); sensitivity to keys
+    gp2 = algorithm.FusedGeneticProgramming(f0, md, mutation_rate=0.25, survival_rate=0.3, elite_rate=0.01)
+    f1b = gp2.step(fit, keys)
+    assert G.same_bits(f1b.batch_node_value, v1) and G.same_bits(f1b.batch_subtree_size, s1)
+    f1c = algorithm.FusedGeneticProgramming(f0, md, 0.25, 0.3, elite_rate=0.01).step(fit, torch.tensor([11, 23], dtype=torch.uint32, device="cuda"))
+    assert not G.same_bits(f1c.batch_node_value, v1)
+    # it evolves: XOR-ish regression improves under the fused loop
+    X = torch.rand(256, 3, device="cuda") * 2 - 1
+    y = (X[:, :1] * X[:, 1:2] + X[:, 2:3]).contiguous()
+    prob = problem.SymbolicRegression(datapoints=X, labels=y)
+    gp3 = algorithm.FusedGeneticProgramming(tree.Forest.random_generate(5000, d), d.update(max_layer_cnt=3), 0.2, 0.3, elite_rate=0.01)
+    best = []
+    for _ in range(12):
+        fitness = prob.evaluate(gp3.forest)
+        best.append(float(torch.nan_to_num(fitness, nan=float("-inf")).max()))
+        gp3.step(fitness)
+        orc.check_forest(*host(gp3.forest), input_len=3)
+    assert all(b2 >= b1 for b1, b2 in zip(best, best[1:])) and best[-1] > best[0]
