@@ -2,4 +2,4 @@ from .selection import BaseSelection, DefaultSelection  # noqa: F401
 from .crossover import BaseCrossover, DefaultCrossover  # noqa: F401
 from .mutation import BaseMutation, DefaultMutation  # noqa: F401
 from .genetic_programming import GeneticProgramming, ParetoFront  # noqa: F401
-from .fused import FusedGeneticProgramming  # noqa: F401
+from .fused import FusedGeneticProgramming, GraphedGeneration  # noqa: F401

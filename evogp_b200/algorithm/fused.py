@@ -50,3 +50,48 @@ class FusedGeneticProgramming:
         self.forest = Forest(f.input_len, f.output_len, v, t, s)
         self.generation += 1
         return self.forest
+
+
+class GraphedGeneration:
+    """A whole generation — evaluate the population, sort, build the next one — captured ONCE as a CUDA graph and
+    replayed per generation (every shape on this path is static, nothing synchronises with the host).  The population
+    lives in fixed buffers that the graph updates in place; `fitness` holds the fitness of the population that was
+    evaluated by the last replay (i.e. of the PREVIOUS generation's trees).
+
+        gen = GraphedGeneration(FusedGeneticProgramming(...), problem)
+        for _ in range(100):
+            gen.replay()
+        best = gen.fitness.max()
+    """
+
+    def __init__(self, algorithm: FusedGeneticProgramming, problem, warmup: int = 3):
+        self.algorithm = algorithm
+        self.problem = problem
+        f = algorithm.forest
+        self.forest = Forest(f.input_len, f.output_len, f.batch_node_value.clone(), f.batch_node_type.clone(),
+                             f.batch_subtree_size.clone())
+        algorithm.forest = self.forest
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the capture stream, as torch.cuda.graph requires
+            for _ in range(warmup):
+                self._one_generation()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.fitness = self._one_generation()
+
+    def _one_generation(self):
+        fitness = self.problem.evaluate(self.forest)
+        self.algorithm.forest = self.forest
+        nxt = self.algorithm.step(fitness)
+        self.forest.batch_node_value.copy_(nxt.batch_node_value)
+        self.forest.batch_node_type.copy_(nxt.batch_node_type)
+        self.forest.batch_subtree_size.copy_(nxt.batch_subtree_size)
+        self.algorithm.forest = self.forest
+        return fitness
+
+    def replay(self):
+        self.graph.replay()
+        self.algorithm.generation += 1
+        return self.fitness

@@ -272,3 +272,30 @@ def test_fused_generation_step(api, orc):
         gp3.step(fitness)
         orc.check_forest(*host(gp3.forest), input_len=3)
     assert all(b2 >= b1 for b1, b2 in zip(best, best[1:])) and best[-1] > best[0]
+
+
+def test_generation_as_cuda_graph(api, orc):
+    """evaluate + sort + next-generation captured once, replayed per generation: same evolution as eager execution."""
+    tree, algorithm, problem, _ = api
+    d = tree.GenerateDescriptor(max_tree_len=64, input_len=3, output_len=1, using_funcs=["+", "-", "*", "/"], max_layer_cnt=6,
+                                const_samples=[-1, 0, 1])
+    X = torch.rand(512, 3, device="cuda") * 2 - 1
+    y = (X[:, :1] ** 4 / (X[:, :1] ** 4 + 1) + torch.sin(3 * X[:, 1:2]) * X[:, 2:3]).contiguous()
+    prob = problem.SymbolicRegression(datapoints=X, labels=y)
+    torch.manual_seed(9)
+    gp = algorithm.FusedGeneticProgramming(tree.Forest.random_generate(8000, d), d.update(max_layer_cnt=3), 0.2, 0.3, elite_rate=0.01)
+    gen = algorithm.GraphedGeneration(gp, prob)
+    best = []
+    for _ in range(15):
+        fit = gen.replay()
+        best.append(float(torch.nan_to_num(fit, nan=float("-inf")).max()))
+    torch.cuda.synchronize()
+    orc.check_forest(*host(gen.forest), input_len=3)
+    assert all(b2 >= b1 - 1e-12 for b1, b2 in zip(best, best[1:])) and best[-1] >= best[0]   # elitism: never regresses
+    # the fitness tensor really is the fitness of the population the replay evaluated
+    f_before = host(gen.forest)
+    fit = gen.replay().clone()
+    torch.cuda.synchronize()
+    want = -orc.sr_fitness(*f_before, X.cpu().numpy(), y.cpu().numpy(), nthreads=8)
+    ok = np.isfinite(want) & (np.abs(want) < 1e6)
+    G.assert_close_fitness(fit[torch.from_numpy(ok)], want[ok], rtol=2e-3, what="graphed generation fitness")

@@ -83,7 +83,7 @@ def main():
           f"mean_len now {algo.forest.batch_subtree_size[:, 0].float().mean():.1f}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and (len(sys.argv) <= 3):
     main()
 
 
@@ -134,3 +134,38 @@ def gp_phase_breakdown(P=100000, V=3):
 
 if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[3] == "phases":
     gp_phase_breakdown(int(sys.argv[1]), int(sys.argv[2]))
+
+
+def fused_loop(P=100000, V=3, G=20):
+    """Generations per second of the reference-equivalent loop vs the fused step (same algorithm, different RNG stream)."""
+    from evogp_b200.algorithm import FusedGeneticProgramming
+    L, N = 64, 1024
+    torch.manual_seed(0)
+    desc = GenerateDescriptor(max_tree_len=L, input_len=V, output_len=1, using_funcs=["+", "-", "*", "/"], max_layer_cnt=6,
+                              const_samples=[-1, 0, 1])
+    X = torch.rand(N, V, device="cuda") * 2 - 1
+    y = (X[:, :1] ** 2 + X[:, 1:2]).contiguous()
+    prob = SymbolicRegression(datapoints=X, labels=y)
+    for name in ("unfused", "fused"):
+        f = Forest.random_generate(P, desc)
+        if name == "fused":
+            algo = FusedGeneticProgramming(f, desc.update(max_layer_cnt=3), 0.2, 0.3, elite_rate=0.01)
+        else:
+            algo = GeneticProgramming(f, DefaultCrossover(), DefaultMutation(0.2, desc.update(max_layer_cnt=3)),
+                                      DefaultSelection(survival_rate=0.3, elite_rate=0.01))
+        for _ in range(3):
+            algo.step(prob.evaluate(algo.forest))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); te = 0.0
+        for _ in range(G):
+            a = time.perf_counter(); fit = prob.evaluate(algo.forest); torch.cuda.synchronize(); te += time.perf_counter() - a
+            algo.step(fit)
+        torch.cuda.synchronize()
+        tot = (time.perf_counter() - t0) / G
+        best = float(torch.nan_to_num(prob.evaluate(algo.forest), nan=float("-inf")).max())
+        print(f"{name:8s} P={P}: {tot * 1e3:.3f} ms/generation (evaluate {te / G * 1e3:.3f} ms, step {(tot - te / G) * 1e3:.3f} ms), "
+              f"mean_len {algo.forest.batch_subtree_size[:, 0].float().mean():.1f}, best fitness {best:.4g}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[3] == "fused":
+    fused_loop(int(sys.argv[1]), int(sys.argv[2]))
