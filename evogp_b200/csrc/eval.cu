@@ -467,16 +467,21 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     const int SLOT = K * 32;
     a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
     a.NP = a.npass * SLOT;
-    a.depth = depth > kRegSlots ? depth - kRegSlots : 1;   // slots 0/1 live in registers
+    a.depth = MULTI ? 1 : (depth > kRegSlots ? depth - kRegSlots : 1);   // multi-output programs use no operand stack
     depth = a.depth;
     auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
     // the dataset slice a launch stages: all of it when it fits next to >= 4 warps, else whole passes of it
     const size_t per_dp = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * 4;   // bytes per datapoint
     const int N_total = a.N;
     int tile = a.NP;                                                                         // datapoints per launch
-    if (per_dp && per_dp * tile + 4 * per_warp() > (size_t)g_max_smem) {
-        const size_t room = (size_t)g_max_smem > 4 * per_warp() ? (size_t)g_max_smem - 4 * per_warp() : 0;
+    // one launch when the dataset leaves room for two 8-warp CTAs per SM; otherwise tiles of <= 48 KB of dataset so
+    // that occupancy survives (a 164 KB tile would leave one 4-warp CTA per SM: measured 6x slower on configs[3])
+    if (per_dp && 2 * (per_dp * tile + 8 * per_warp() + 1024) > (size_t)g_max_smem) {
+        size_t room = 48 * 1024;
+        if (room + 4 * per_warp() > (size_t)g_max_smem) room = (size_t)g_max_smem > 4 * per_warp() ? (size_t)g_max_smem - 4 * per_warp() : 0;
         tile = (int)(room / per_dp / SLOT) * SLOT;
+        if (tile < SLOT) tile = ((size_t)SLOT * per_dp + 4 * per_warp() <= (size_t)g_max_smem) ? SLOT : 0;
+        if (tile >= a.NP) tile = a.NP;
         if (tile < SLOT || (a.N + tile - 1) / tile > 64) {
             set_error("%d inputs + %d labels per datapoint do not fit the %d B shared-memory staging area", a.V, a.O, g_max_smem);
             return EVOGP_ERR_UNSUPPORTED;

@@ -6,6 +6,7 @@
 // node_type rows plus ONE length per tree (column 0 of subtree_size, gathered on
 // the host into a pinned staging array) — 6 B per node slot instead of 8.
 // Staging buffers are cached across calls.
+#include <cstdlib>
 #include <mutex>
 #include "common.cuh"
 
@@ -98,7 +99,9 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     EVOGP_REQUIRE(popSize > 0 && dataPoints > 0 && gpLen > 0 && varLen > 0 && outLen > 0, "empty problem");
     std::lock_guard<std::mutex> lk(g_mu);
     // chunk so that a few chunks are in flight even for small populations, capped at 64 Ki rows
-    size_t rows = (popSize + 7) / 8;
+    // (EVOGP_HOST_CHUNKS overrides the default of 8 chunks; tuning knob)
+    static const int n_chunks = [] { const char *e = getenv("EVOGP_HOST_CHUNKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+    size_t rows = (popSize + n_chunks - 1) / n_chunks;
     if (rows < 4096) rows = popSize < 4096 ? popSize : 4096;
     if (rows > 65536) rows = 65536;
     const size_t L = gpLen;
