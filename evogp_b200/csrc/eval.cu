@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 #include "lower.cuh"
 #include "fastpath_k8.inc"
+#include "fastpath_k8_tmem.inc"
 
 namespace evogp {
 
@@ -41,6 +42,8 @@ struct ReplayArgs {
     int P, Lp, N, V, O;
     int NP;                 // N rounded up to a whole number of passes
     int npass, depth, mode;
+    int smem_depth;         // operand-stack slots per warp kept in shared memory (0 when the stack is in tensor memory)
+    int tmem_cols;          // TSTK: tensor-memory columns the CTA allocates (power of two >= 32)
     // datapoint tiling (dataset larger than the shared-memory staging area): this launch covers datapoints
     // [d_base, d_base + N) of N_total; loss modes carry the running sum in out[] between launches
     int d_base, N_total, first_tile, last_tile;
@@ -72,6 +75,22 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Tensor memory as a per-lane scratch: a warp owns TMEM lanes 32 * (warp % 4) .. + 31, thread i <-> lane i, and
+// the .32x32b.x8 shapes move 8 consecutive 32-bit columns of every lane to / from 8 registers per thread.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
+                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(float (&v)[8], uint32_t taddr) {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
                  : "memory");
 }
 
@@ -108,8 +127,10 @@ __device__ __forceinline__ int dp_index(int lane, int k) {
     else return k * 32 + lane;
 }
 
-template <int K, bool MULTI, bool ROWWISE>
-__global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
+// TSTK: the operand stack lives in tensor memory instead of shared memory (K == 8, single-output only)
+template <int K, bool MULTI, bool ROWWISE, bool TSTK = false>
+__global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g) {
+    static_assert(!TSTK || (K == 8 && !MULTI && !ROWWISE), "tensor-memory stack: K = 8 single-output only");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int VW = K >= 4 ? 4 : 1;
     constexpr int SLOT = K * 32;                 // floats per stack slot / per output accumulator
@@ -122,8 +143,8 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
     float *after = Ys + ((g.mode <= MODE_ABS) ? (size_t)g.O * g.NP : 0);
     uint2 *progs = reinterpret_cast<uint2 *>(after) + (size_t)warp * 2 * g.Lp;          // 2 rows / warp
     float *stacks = reinterpret_cast<float *>(reinterpret_cast<uint2 *>(after) + (size_t)nwarp * 2 * g.Lp);
-    float *stack = stacks + (size_t)warp * g.depth * SLOT;
-    float *outs_all = stacks + (size_t)nwarp * g.depth * SLOT;          // [O][SLOT] / warp (MULTI)
+    float *stack = stacks + (size_t)warp * g.smem_depth * SLOT;
+    float *outs_all = stacks + (size_t)nwarp * g.smem_depth * SLOT;     // [O][SLOT] / warp (MULTI)
     float *outs = outs_all + (MULTI ? (size_t)warp * g.O * SLOT : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(outs_all + (MULTI ? (size_t)nwarp * g.O * SLOT : 0)) + warp * 2;
 
@@ -147,7 +168,23 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
         mbar_init(bars + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // tensor-memory operand stack: warp 0 allocates the CTA's columns; warp w uses lanes 32 * (w % 4) and the
+    // column block (w / 4) * depth * 8
+    __shared__ uint32_t tmem_base_slot;
+    uint32_t tstack = 0;
+    if constexpr (TSTK) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                         "r"((uint32_t)g.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
     __syncthreads();
+    if constexpr (TSTK) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.depth * 8u;
+    }
 
     const uint32_t row_bytes = (uint32_t)g.Lp * 8u;
     uint32_t phase0 = 0, phase1 = 0;
@@ -199,11 +236,13 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
             int pc = 0;
             // operand-stack slots are static (program.cuh): 0 -> bankB, 1 -> bankC, s >= 2 -> shared memory
             auto slot_store = [&](int slot) {
+                if constexpr (TSTK) { tmem_st8(tstack + (uint32_t)slot * 8u, acc); return; }
                 if (slot == 0 && kRegSlots > 0) { FOR_K bankB[k] = acc[k]; }
                 else if (slot == 1 && kRegSlots > 1) { FOR_K bankC[k] = acc[k]; }
                 else st_vec<K>(stack + (slot - kRegSlots) * SLOT + lane_off, acc);
             };
             auto slot_load = [&](float(&d)[K], int slot) {
+                if constexpr (TSTK) { tmem_ld8(d, tstack + (uint32_t)slot * 8u); return; }
                 if (slot == 0 && kRegSlots > 0) { FOR_K d[k] = bankB[k]; }
                 else if (slot == 1 && kRegSlots > 1) { FOR_K d[k] = bankC[k]; }
                 else ld_vec<K>(d, stack + (slot - kRegSlots) * SLOT + lane_off);
@@ -309,15 +348,24 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
 
             if constexpr (K == 8 && !MULTI && !ROWWISE) {
                 // PTX fast path (fastpath_k8.inc): brx.idx jump table, operands by opcode
-                const uint32_t prog_base = smem_u32(prog), stack_base = smem_u32(stack + lane_off);
+                const uint32_t prog_base = smem_u32(prog);
+                const uint32_t stack_base = TSTK ? tstack : smem_u32(stack + lane_off);
                 uint32_t pc_addr = prog_base, status;
                 const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
                 for (;;) {
-                    asm volatile(EVOGP_FASTPATH_K8_ASM
-                                 : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
-                                   "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
-                                 : "r"(xl_addr), "r"(npb), "r"(stack_base)
-                                 : "memory");
+                    if constexpr (TSTK) {
+                        asm volatile(EVOGP_FASTPATH_K8_TMEM_ASM
+                                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                       "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
+                                     : "r"(xl_addr), "r"(npb), "r"(stack_base), "r"(stack_base - 8u)
+                                     : "memory");
+                    } else {
+                        asm volatile(EVOGP_FASTPATH_K8_ASM
+                                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                       "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
+                                     : "r"(xl_addr), "r"(npb), "r"(stack_base)
+                                     : "memory");
+                    }
                     if (status == 0) break;
                     pc = (int)((pc_addr - prog_base) >> 3);
                     if (step()) break;
@@ -385,12 +433,22 @@ __global__ void __launch_bounds__(256, 2) replay_kernel(ReplayArgs g) {
         buf ^= 1;
         tree = next;
     }
+    if constexpr (TSTK) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "r"((uint32_t)g.tmem_cols)
+                         : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static int g_sm_count = 0, g_max_smem = 0;
+static int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
+// EVOGP_TMEM_STACK=0 keeps the operand stack in shared memory (the A/B switch of profiles/; default on)
+static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_STACK"); return !(e && e[0] == '0'); }();
 // optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
 
@@ -400,6 +458,7 @@ static int device_props() {
     EVOGP_CUDA(cudaGetDevice(&dev));
     EVOGP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     EVOGP_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    EVOGP_CUDA(cudaDeviceGetAttribute(&g_smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     return EVOGP_OK;
 }
 
@@ -439,8 +498,19 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
     a.rows_have_sizes = len_stride != 1;
+    // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
+    // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
+    static int per_sm_cached[2] = {0, 0};
+    static size_t per_sm_smem[2] = {~(size_t)0, ~(size_t)0};
+    if (per_sm_smem[MULTI] != smem) {
+        int n = 0;
+        EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lower_kernel<MULTI>, warps * 32, smem));
+        per_sm_cached[MULTI] = n < 1 ? 1 : n;
+        per_sm_smem[MULTI] = smem;
+    }
+    const int per_sm = per_sm_cached[MULTI];
     long long grid = ((long long)P + warps - 1) / warps;
-    const long long cap = (long long)g_sm_count * (2048 / (warps * 32));
+    const long long cap = (long long)g_sm_count * per_sm;
     if (grid > cap) grid = cap;
     lower_kernel<MULTI><<<(unsigned)grid, warps * 32, smem, st>>>(a);
     count_launch();
@@ -461,15 +531,26 @@ static int choose_k(int N) {
     return best;
 }
 
-template <int K, bool MULTI, bool ROWWISE>
+// tensor-memory columns a CTA of `warps` warps needs for operand stacks of `depth` slots (8 columns per slot; the
+// warps of one lane quarter share the columns), as the power of two >= 32 tcgen05.alloc accepts
+static int tmem_stack_cols(int warps, int depth) {
+    const int need = ((warps + 3) / 4) * depth * 8;
+    int cols = 32;
+    while (cols < need) cols <<= 1;
+    return cols;
+}
+
+template <int K, bool MULTI, bool ROWWISE, bool TSTK = false>
 static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
-    auto kern = replay_kernel<K, MULTI, ROWWISE>;
+    auto kern = replay_kernel<K, MULTI, ROWWISE, TSTK>;
     const int SLOT = K * 32;
     a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
     a.NP = a.npass * SLOT;
     a.depth = MULTI ? 1 : (depth > kRegSlots ? depth - kRegSlots : 1);   // multi-output programs use no operand stack
     depth = a.depth;
-    auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
+    a.smem_depth = TSTK ? 0 : depth;
+    a.tmem_cols = 0;
+    auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)a.smem_depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
     // the dataset slice a launch stages: all of it when it fits next to >= 4 warps, else whole passes of it
     const size_t per_dp = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * 4;   // bytes per datapoint
     const int N_total = a.N;
@@ -501,11 +582,26 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         const size_t data = per_dp * a.NP;
         int warps = 8;
         while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
-        const size_t smem = data + warps * per_warp();
+        size_t smem = data + warps * per_warp();
         EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
         if (per_sm < 1) per_sm = 1;
+        if constexpr (TSTK) {
+            // The occupancy API answers 1 CTA/SM for a kernel that allocates tensor memory; the real limits are
+            // registers, shared memory and the 512 columns (every resident CTA holds its columns until it exits,
+            // and tcgen05.alloc blocks when they run out - CTAs beyond `fit` would only wait).
+            a.tmem_cols = tmem_stack_cols(warps, depth);
+            const int fit = 512 / a.tmem_cols;
+            cudaFuncAttributes fa;
+            EVOGP_CUDA(cudaFuncGetAttributes(&fa, kern));
+            const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+            const int by_regs = 65536 / (regs_per_warp * warps);
+            const int by_smem = (int)((size_t)g_smem_per_sm / (smem + fa.sharedSizeBytes + 1024));
+            per_sm = fit < by_regs ? fit : by_regs;
+            if (by_smem < per_sm) per_sm = by_smem;
+            if (per_sm < 1) per_sm = 1;
+        }
         long long want = ((long long)a.P + warps - 1) / warps;
         int grid = (int)(want < (long long)per_sm * g_sm_count ? want : (long long)per_sm * g_sm_count);
         if (grid < 1) grid = 1;
@@ -522,7 +618,13 @@ template <bool MULTI>
 static int launch_replay(const ReplayArgs &a, int depth, cudaStream_t st) {
     if (a.mode == MODE_ROWWISE) return launch_replay_t<1, MULTI, true>(a, depth, st);
     switch (choose_k(a.N)) {
-    case 8: return launch_replay_t<8, MULTI, false>(a, depth, st);
+    case 8:
+        if constexpr (!MULTI) {
+            // operand stack in tensor memory while two warps per lane quarter fit 128 columns (depth <= 8, i.e.
+            // max_tree_len <= 256); deeper stacks keep the shared-memory kernel
+            if (tmem_stack_cols(8, depth > 0 ? depth : 1) <= 128 && g_use_tmem_stack) return launch_replay_t<8, false, false, true>(a, depth, st);
+        }
+        return launch_replay_t<8, MULTI, false>(a, depth, st);
     case 4: return launch_replay_t<4, MULTI, false>(a, depth, st);
     default: return launch_replay_t<1, MULTI, false>(a, depth, st);
     }

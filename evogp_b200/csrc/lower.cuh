@@ -195,8 +195,8 @@ struct LowerScratch {
     uint16_t *s;     // subtree sizes
     uint16_t *M;     // marks -> exclusive prefix sum of instruction slots
     uint32_t *D;     // path-sum workspace: [L + 1]
-    uint16_t *q;     // value children: rank [0:2) | slots emitted before this child among its siblings [2:13) | valid [15]
-    uint16_t *st;    // start slot [0:11) | acc live [11] | stack height [12:16)
+    uint16_t *q;     // value children: rank [0:2) | valid [15]
+    uint16_t *st;    // spare (kept so the scratch layout is stable)
 };
 __host__ __device__ inline size_t lower_scratch_bytes(int L) { return (size_t)L * 18 + 32; }   // 4+2+2 rows, 2+4+2+2 aux
 // the part that is not the staged rows: M, D, q, st
@@ -240,12 +240,11 @@ __host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
 #endif
 }
 
-// Stage the row and make sure s[] holds arity-consistent subtree sizes.  Returns false for a malformed row.
-// val == nullptr: the rows are already staged in k.t / k.v (/ k.s) — the fused kernel's TMA path.
+// Stage the row into k.t / k.v / k.s.  Returns false when the length is impossible.
+// val == nullptr: the rows are already staged in k.t / k.v (/ k.s).
 // size == nullptr with val != nullptr, or have_sizes == false: no size row; sizes are recomputed from the arities.
-template <bool MULTI>
-__host__ __device__ inline bool lower_stage(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
-                                            int L, LowerScratch k, bool have_sizes) {
+__host__ __device__ inline bool stage_rows(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
+                                           int L, LowerScratch k, bool have_sizes) {
     if (len < 1 || len > L) return false;
     if (val) {
         for (int j = ln.lane; j < len; j += ln.n) {
@@ -257,6 +256,36 @@ __host__ __device__ inline bool lower_stage(Lanes ln, const float *val, const in
         for (int j = ln.lane; j < len; j += ln.n) k.s[j] = 0;
     }
     lanes_sync();
+    return true;
+}
+
+// Stale or inconsistent sizes: recompute them from the arities, leaves -> root (one lane; rare).
+// Returns false when the prefix does not close at len (a malformed row).
+template <bool MULTI>
+__host__ __device__ inline bool fix_sizes(Lanes ln, int len, LowerScratch k) {
+    bool ok = true;
+    if (ln.lane == 0) {
+        for (int i = len - 1; i >= 0 && ok; --i) {
+            const int ar = arity_of(k.t[i], MULTI);
+            int c = i + 1, tot = 1;
+            for (int a = 0; a < ar; ++a) {
+                if (c >= len) { ok = false; break; }
+                tot += k.s[c];
+                c += k.s[c];
+            }
+            k.s[i] = (uint16_t)tot;
+        }
+        if (ok && (int)k.s[0] != len) ok = false;
+    }
+    lanes_sync();
+    return !lanes_any(!ok);
+}
+
+// Stage the row and make sure s[] holds arity-consistent subtree sizes.  Returns false for a malformed row.
+template <bool MULTI>
+__host__ __device__ inline bool lower_stage(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
+                                            int L, LowerScratch k, bool have_sizes) {
+    if (!stage_rows(ln, val, typ, size, len, L, k, have_sizes)) return false;
     // verify: every function node's size is 1 + its children's, children stay inside the row, root spans it
     bool bad = false;
     for (int j = ln.lane; j < len; j += ln.n) {
@@ -273,23 +302,7 @@ __host__ __device__ inline bool lower_stage(Lanes ln, const float *val, const in
     }
     if (ln.lane == 0 && (int)k.s[0] != len) bad = true;
     if (!lanes_any(bad)) return true;
-    // stale or inconsistent sizes: recompute them from the arities, leaves -> root (one lane; rare)
-    bool ok = true;
-    if (ln.lane == 0) {
-        for (int i = len - 1; i >= 0 && ok; --i) {
-            const int ar = arity_of(k.t[i], MULTI);
-            int c = i + 1, tot = 1;
-            for (int a = 0; a < ar; ++a) {
-                if (c >= len) { ok = false; break; }
-                tot += k.s[c];
-                c += k.s[c];
-            }
-            k.s[i] = (uint16_t)tot;
-        }
-        if (ok && (int)k.s[0] != len) ok = false;   // the prefix does not close at len
-    }
-    lanes_sync();
-    return !lanes_any(!ok);
+    return fix_sizes<MULTI>(ln, len, k);
 }
 
 __host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
@@ -303,12 +316,53 @@ __host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
 __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
                                                  int len, int L, int Lp, int V, int depth_budget, uint2 *out,
                                                  LowerScratch k, bool have_sizes) {
-    if (!lower_stage<false>(ln, val, typ, size, len, L, k, have_sizes)) {
+    if (!stage_rows(ln, val, typ, size, len, L, k, have_sizes)) {
         emit_nan(ln, out, Lp);
         return -1;
     }
     auto is_func = [&](int j) { return arity_of(k.t[j], false) != 0; };
     auto is_const = [&](int j) { return (k.t[j] & NT_MASK) == NT_CONST; };
+    // ---- one pass: verify the sizes (every function node's size is 1 + its children's, children stay inside
+    //      the row, the root spans it) and mark the instruction slots each node contributes itself.  Stale or
+    //      absent sizes are recomputed once by fix_sizes and the pass repeats. ----
+    for (int attempt = 0;; ++attempt) {
+        bool bad = false;
+        for (int i = ln.lane; i < len; i += ln.n) {
+            const int ar = arity_of(k.t[i], false);
+            int c[3], tot = 1, pos = i + 1;
+            bool mine = false;
+            for (int a = 0; a < ar; ++a) {
+                if (pos >= len) { mine = true; break; }
+                const int cs = k.s[pos];
+                if (cs < 1) { mine = true; break; }
+                c[a] = pos;
+                tot += cs;
+                pos += cs;
+            }
+            if ((int)k.s[i] != tot || i + tot > len) mine = true;
+            int m = 0;
+            if (!mine) {
+                if (ar == 1) m = 1;
+                else if (ar == 2)    // two constants: LOAD + AK
+                    m = (!is_func(c[0]) && !is_func(c[1]) && is_const(c[0]) && is_const(c[1])) ? 2 : 1;
+                else if (ar == 3)    // every leaf child is a LOAD
+                    m = 1 + (!is_func(c[0])) + (!is_func(c[1])) + (!is_func(c[2]));
+            }
+            bad |= mine;
+            k.M[i] = (uint16_t)m;
+            k.q[i] = 0;
+            k.D[i] = 0;
+        }
+        if (ln.lane == 0) {
+            k.D[len] = 0;
+            if ((int)k.s[0] != len) bad = true;
+        }
+        if (!lanes_any(bad)) break;
+        if (attempt || !fix_sizes<false>(ln, len, k)) {
+            emit_nan(ln, out, Lp);
+            return -1;
+        }
+    }
     if (!is_func(0)) {   // the tree is a single leaf
         if (ln.lane == 0) {
             out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[0], bits_f32(k.v[0]), V), 0);
@@ -316,95 +370,69 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
         }
         return 0;
     }
-    // ---- marks: instruction slots each node contributes itself ----
-    for (int i = ln.lane; i < len; i += ln.n) {
-        const int ar = arity_of(k.t[i], false);
-        int m = 0;
-        if (ar == 1) m = 1;
-        else if (ar == 2) {
-            const int x = i + 1, y = x + k.s[x];
-            m = (!is_func(x) && !is_func(y) && is_const(x) && is_const(y)) ? 2 : 1;   // two constants: LOAD + AK
-        } else if (ar == 3) {
-            const int a = i + 1, b = a + k.s[a], c = b + k.s[b];
-            m = 1 + (!is_func(a)) + (!is_func(b)) + (!is_func(c));                     // every leaf child is a LOAD
-        }
-        k.M[i] = (uint16_t)m;
-        k.q[i] = 0;
-    }
     lanes_sync();
     lanes_exclusive_scan(ln, k.M, len);
     auto ni = [&](int j) { return (int)k.M[j + k.s[j]] - (int)k.M[j]; };   // slots of the whole subtree j
     // ---- rank the value-producing children of every function node: larger subtree first
     //      (ties: later child first, the reference's order), so the lighter sibling is the one evaluated
-    //      with a value pending and the operand stack stays O(log len) deep (stack_depth_bound) ----
+    //      with a value pending and the operand stack stays O(log len) deep (stack_depth_bound).
+    //      In the same pass, root -> leaves as one prefix sum.  For a value child j (rank r, `before` slots
+    //      emitted ahead of it among its siblings):  start(j) = sum of `before` over the path root..j;
+    //      pending(j) = sum of r over that path = values alive (in acc or on the stack) when subtree j begins,
+    //      so acc is live iff pending > 0 and the stack height is pending - 1.  A path sum in prefix order is a
+    //      prefix sum of "add at j, subtract at j + size[j]" (j's contribution covers exactly its span). ----
+    auto place = [&](int ch, uint32_t r, uint32_t before) {
+        k.q[ch] = (uint16_t)(r | 0x8000);
+        const uint32_t add = before | (r << 16);
+        if (add) {
+            lanes_atomic_add(&k.D[ch], add);
+            lanes_atomic_add(&k.D[ch + k.s[ch]], 0u - add);
+        }
+    };
     for (int i = ln.lane; i < len; i += ln.n) {
         const int ar = arity_of(k.t[i], false);
         if (ar == 0) continue;
-        int c[3], n = 0;
-        c[0] = i + 1;
-        if (ar > 1) c[1] = c[0] + k.s[c[0]];
-        if (ar > 2) c[2] = c[1] + k.s[c[1]];
-        if (ar == 3) {
+        const int c0 = i + 1;
+        if (ar == 1) {
+            if (is_func(c0)) k.q[c0] = 0x8000;
+        } else if (ar == 2) {
+            const int c1 = c0 + k.s[c0];
+            const bool f0 = is_func(c0), f1 = is_func(c1);
+            if (f0 && f1) {
+                const bool x_first = k.s[c0] > k.s[c1];
+                const int first = x_first ? c0 : c1, second = x_first ? c1 : c0;
+                k.q[first] = 0x8000;
+                place(second, 1, (uint32_t)ni(first));
+            } else if (f0 || f1) {
+                k.q[f0 ? c0 : c1] = 0x8000;
+            }
+        } else {
+            const int c1 = c0 + k.s[c0], c2 = c1 + k.s[c1];
+            const int c[3] = {c0, c1, c2};
             int o0 = 2, o1 = 1, o2 = 0;   // c, b, a; stable bubble sort by size, descending
             if (k.s[c[o1]] > k.s[c[o0]]) { const int sw = o0; o0 = o1; o1 = sw; }
             if (k.s[c[o2]] > k.s[c[o1]]) { const int sw = o1; o1 = o2; o2 = sw; }
             if (k.s[c[o1]] > k.s[c[o0]]) { const int sw = o0; o0 = o1; o1 = sw; }
             const int ord[3] = {o0, o1, o2};
-            int before = 0;
+            uint32_t before = 0;
             for (int r = 0; r < 3; ++r) {
-                const int ch = ord[r] == 0 ? c[0] : (ord[r] == 1 ? c[1] : c[2]);
-                k.q[ch] = (uint16_t)(r | (before << 2) | 0x8000);
-                before += is_func(ch) ? ni(ch) : 1;
+                const int ch = ord[r] == 0 ? c0 : (ord[r] == 1 ? c1 : c2);
+                place(ch, (uint32_t)r, before);
+                before += is_func(ch) ? (uint32_t)ni(ch) : 1u;
             }
-        } else {
-            for (int a = 0; a < ar; ++a)
-                if (is_func(c[a])) ++n;
-            if (ar == 1) {
-                if (n) k.q[c[0]] = 0x8000;
-            } else if (n == 1) {
-                const int ch = is_func(c[0]) ? c[0] : c[1];
-                k.q[ch] = 0x8000;
-            } else if (n == 2) {
-                const bool x_first = k.s[c[0]] > k.s[c[1]];
-                const int first = x_first ? c[0] : c[1], second = x_first ? c[1] : c[0];
-                k.q[first] = 0x8000;
-                k.q[second] = (uint16_t)(1 | (ni(first) << 2) | 0x8000);
-            }
-        }
-    }
-    // ---- root -> leaves in one prefix sum.  For a value child j (rank r, `before` slots emitted ahead of it
-    //      among its siblings):  start(j) = sum of `before` over the path root..j;  pending(j) = sum of r over
-    //      that path = values alive (in acc or on the stack) when subtree j begins, so acc is live iff
-    //      pending > 0 and the stack height is pending - 1.  A path sum in prefix order is a prefix sum of
-    //      "add at i, subtract at i + size[i]" (i's contribution covers exactly its subtree span). ----
-    for (int i = ln.lane; i <= len; i += ln.n) k.D[i] = 0;
-    lanes_sync();
-    for (int i = ln.lane; i < len; i += ln.n) {
-        const uint32_t qq = k.q[i];
-        if (!(qq & 0x8000)) continue;
-        const uint32_t add = ((qq >> 2) & 0x7FF) | ((qq & 3) << 16);    // before | rank << 16
-        if (add) {
-            lanes_atomic_add(&k.D[i], add);
-            lanes_atomic_add(&k.D[i + k.s[i]], 0u - add);
         }
     }
     lanes_sync();
     lanes_inclusive_scan32(ln, k.D, len);
-    for (int i = ln.lane; i < len; i += ln.n) {
-        const uint32_t d = k.D[i], pending = d >> 16;
-        const uint32_t live = pending ? 1u : 0u, h = pending ? pending - 1 : 0u;
-        k.st[i] = (uint16_t)((d & 0x7FF) | (live << 11) | (h << 12));
-    }
-    lanes_sync();
     // ---- emit ----
     int my_max = 0;
     for (int i = ln.lane; i < len; i += ln.n) {
         const int ar = arity_of(k.t[i], false);
         const bool valued = i == 0 || (k.q[i] & 0x8000);
         if (!valued) continue;                    // folded leaf: an operand of its parent
-        const uint32_t sb = k.st[i];
-        const int st = sb & 0x7FF;
-        const uint32_t live = (sb >> 11) & 1, height = (sb >> 12) & 0xF;
+        const uint32_t d = k.D[i], pending = d >> 16;
+        const int st = d & 0xFFFF;
+        const uint32_t live = pending ? 1u : 0u, height = pending ? pending - 1 : 0u;
         const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
         const uint32_t height_in = height + live;
         if (live) my_max = my_max > (int)height + 1 ? my_max : (int)height + 1;
@@ -548,7 +576,7 @@ struct LowerArgs {
 
 // one warp per tree, grid-stride over the population
 template <bool MULTI>
-__global__ void __launch_bounds__(256) lower_kernel(LowerArgs g) {
+__global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
     extern __shared__ __align__(16) unsigned char lower_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const size_t per_warp = (lower_scratch_bytes(g.L) + 15) & ~(size_t)15;
