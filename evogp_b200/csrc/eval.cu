@@ -22,6 +22,7 @@
 #include "lower.cuh"
 #include "fastpath_k8.inc"
 #include "fastpath_k8_tmem.inc"
+#include "fastpath_k16_tmem.inc"
 
 namespace evogp {
 
@@ -80,18 +81,29 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 
 // Tensor memory as a per-lane scratch: a warp owns TMEM lanes 32 * (warp % 4) .. + 31, thread i <-> lane i, and
 // the .32x32b.x8 shapes move 8 consecutive 32-bit columns of every lane to / from 8 registers per thread.
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
                  "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(float (&v)[8], uint32_t taddr) {
-    asm volatile("tcgen05.wait::st.sync.aligned;\n"
-                 "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 "tcgen05.wait::ld.sync.aligned;"
+__device__ __forceinline__ void tmem_ld8(float *v, uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "r"(taddr)
                  : "memory");
+}
+// one operand-stack slot = K columns (K = 8 or 16)
+template <int K>
+__device__ __forceinline__ void tmem_store_slot(uint32_t taddr, const float (&v)[K]) {
+#pragma unroll
+    for (int j = 0; j < K / 8; ++j) tmem_st8(taddr + 8u * j, v + 8 * j);
+}
+template <int K>
+__device__ __forceinline__ void tmem_load_slot(float (&v)[K], uint32_t taddr) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < K / 8; ++j) tmem_ld8(v + 8 * j, taddr + 8u * j);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 #define FOR_K _Pragma("unroll") for (int k = 0; k < K; ++k)
@@ -129,8 +141,9 @@ __device__ __forceinline__ int dp_index(int lane, int k) {
 
 // TSTK: the operand stack lives in tensor memory instead of shared memory (K == 8, single-output only)
 template <int K, bool MULTI, bool ROWWISE, bool TSTK = false>
-__global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g) {
-    static_assert(!TSTK || (K == 8 && !MULTI && !ROWWISE), "tensor-memory stack: K = 8 single-output only");
+__global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K == 8) ? 4 : 2)) replay_kernel(ReplayArgs g) {
+    static_assert(!TSTK || ((K == 8 || K == 16) && !MULTI && !ROWWISE), "tensor-memory stack: K = 8 / 16 single-output only");
+    static_assert(K != 16 || TSTK, "K = 16 exists only with the tensor-memory stack");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int VW = K >= 4 ? 4 : 1;
     constexpr int SLOT = K * 32;                 // floats per stack slot / per output accumulator
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g)
     __syncthreads();
     if constexpr (TSTK) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.depth * 8u;
+        tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.depth * (uint32_t)K;
     }
 
     const uint32_t row_bytes = (uint32_t)g.Lp * 8u;
@@ -236,13 +249,13 @@ __global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g)
             int pc = 0;
             // operand-stack slots are static (program.cuh): 0 -> bankB, 1 -> bankC, s >= 2 -> shared memory
             auto slot_store = [&](int slot) {
-                if constexpr (TSTK) { tmem_st8(tstack + (uint32_t)slot * 8u, acc); return; }
+                if constexpr (TSTK) { tmem_store_slot<K>(tstack + (uint32_t)slot * (uint32_t)K, acc); return; }
                 if (slot == 0 && kRegSlots > 0) { FOR_K bankB[k] = acc[k]; }
                 else if (slot == 1 && kRegSlots > 1) { FOR_K bankC[k] = acc[k]; }
                 else st_vec<K>(stack + (slot - kRegSlots) * SLOT + lane_off, acc);
             };
             auto slot_load = [&](float(&d)[K], int slot) {
-                if constexpr (TSTK) { tmem_ld8(d, tstack + (uint32_t)slot * 8u); return; }
+                if constexpr (TSTK) { tmem_load_slot<K>(d, tstack + (uint32_t)slot * (uint32_t)K); return; }
                 if (slot == 0 && kRegSlots > 0) { FOR_K d[k] = bankB[k]; }
                 else if (slot == 1 && kRegSlots > 1) { FOR_K d[k] = bankC[k]; }
                 else ld_vec<K>(d, stack + (slot - kRegSlots) * SLOT + lane_off);
@@ -346,14 +359,21 @@ __global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g)
                 return false;
             };
 
-            if constexpr (K == 8 && !MULTI && !ROWWISE) {
+            if constexpr ((K == 8 || K == 16) && !MULTI && !ROWWISE) {
                 // PTX fast path (fastpath_k8.inc): brx.idx jump table, operands by opcode
                 const uint32_t prog_base = smem_u32(prog);
                 const uint32_t stack_base = TSTK ? tstack : smem_u32(stack + lane_off);
                 uint32_t pc_addr = prog_base, status;
                 const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
                 for (;;) {
-                    if constexpr (TSTK) {
+                    if constexpr (K == 16) {
+                        asm volatile(EVOGP_FASTPATH_K16_TMEM_ASM
+                                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                       "+f"(acc[6]), "+f"(acc[7]), "+f"(acc[8]), "+f"(acc[9]), "+f"(acc[10]), "+f"(acc[11]),
+                                       "+f"(acc[12]), "+f"(acc[13]), "+f"(acc[14]), "+f"(acc[15]), "+r"(pc_addr), "=r"(status)
+                                     : "r"(xl_addr), "r"(npb), "r"(stack_base), "r"(stack_base - 16u)
+                                     : "memory");
+                    } else if constexpr (TSTK) {
                         asm volatile(EVOGP_FASTPATH_K8_TMEM_ASM
                                      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
                                        "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
@@ -392,10 +412,15 @@ __global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g)
                 } else {
                     float y[K];
                     ld_vec<K>(y, Ys + pass_off + lane_off);
-                    FOR_K {
-                        const float diff = y[k] - acc[k];
-                        const float e = g.mode == MODE_MSE ? diff * diff : fabsf(diff);
-                        if (pass_off + dp_index<K>(lane, k) < g.N) err += e;
+                    if (pass_off + SLOT <= g.N) {   // whole pass in range (warp-uniform): no per-datapoint bound checks
+                        if (g.mode == MODE_MSE) { FOR_K { const float diff = y[k] - acc[k]; err += diff * diff; } }
+                        else { FOR_K err += fabsf(y[k] - acc[k]); }
+                    } else {
+                        FOR_K {
+                            const float diff = y[k] - acc[k];
+                            const float e = g.mode == MODE_MSE ? diff * diff : fabsf(diff);
+                            if (pass_off + dp_index<K>(lane, k) < g.N) err += e;
+                        }
                     }
                 }
             } else if (g.mode == MODE_OUTPUT) {
@@ -449,6 +474,7 @@ __global__ void __launch_bounds__(256, TSTK ? 4 : 2) replay_kernel(ReplayArgs g)
 static int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
 // EVOGP_TMEM_STACK=0 keeps the operand stack in shared memory (the A/B switch of profiles/; default on)
 static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_STACK"); return !(e && e[0] == '0'); }();
+static const int g_force_k = []() { const char *e = getenv("EVOGP_REPLAY_K"); return e ? atoi(e) : 0; }();
 // optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
 
@@ -480,18 +506,19 @@ static Workspace carve(void *ws, unsigned P, unsigned L) {
     return w;
 }
 
-template <bool MULTI>
-static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
-                        const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
+template <bool MULTI, bool SPLIT>
+static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
+                          const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
+    auto kern = lower_kernel<MULTI, SPLIT>;
     // one warp per tree; per-warp scratch is 18 B per node slot (lower.cuh)
     const size_t per_warp = (lower_scratch_bytes((int)L) + 15) & ~(size_t)15;
     int warps = 8;
     while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
     const size_t smem = warps * per_warp;
-    static size_t attr_set[2] = {0, 0};
-    if (smem > 48 * 1024 && attr_set[MULTI] < smem) {
-        EVOGP_CUDA(cudaFuncSetAttribute(lower_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[MULTI] = smem;
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && attr_set < smem) {
+        EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
     }
     LowerArgs a;
     a.value = value; a.type = type; a.size = size;
@@ -500,21 +527,29 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
     a.rows_have_sizes = len_stride != 1;
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
-    static int per_sm_cached[2] = {0, 0};
-    static size_t per_sm_smem[2] = {~(size_t)0, ~(size_t)0};
-    if (per_sm_smem[MULTI] != smem) {
+    static int per_sm_cached = 0;
+    static size_t per_sm_smem = ~(size_t)0;
+    if (per_sm_smem != smem) {
         int n = 0;
-        EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lower_kernel<MULTI>, warps * 32, smem));
-        per_sm_cached[MULTI] = n < 1 ? 1 : n;
-        per_sm_smem[MULTI] = smem;
+        EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem));
+        per_sm_cached = n < 1 ? 1 : n;
+        per_sm_smem = smem;
     }
-    const int per_sm = per_sm_cached[MULTI];
     long long grid = ((long long)P + warps - 1) / warps;
-    const long long cap = (long long)g_sm_count * per_sm;
+    const long long cap = (long long)g_sm_count * per_sm_cached;
     if (grid > cap) grid = cap;
-    lower_kernel<MULTI><<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    kern<<<(unsigned)grid, warps * 32, smem, st>>>(a);
     count_launch();
     return check_launch("lower_kernel");
+}
+// split: single-output programs for the K = 16 replay kernel (LOAD + acc-form for operators on leaves)
+template <bool MULTI>
+static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
+                        const int16_t *type, const int16_t *size, int len_stride, int depth, bool split, cudaStream_t st) {
+    if constexpr (!MULTI) {
+        if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, st);
+    }
+    return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, st);
 }
 
 // cost model for choosing K: issue slots per datapoint ~ (dispatch overhead + K) / K, times padding waste
@@ -533,8 +568,8 @@ static int choose_k(int N) {
 
 // tensor-memory columns a CTA of `warps` warps needs for operand stacks of `depth` slots (8 columns per slot; the
 // warps of one lane quarter share the columns), as the power of two >= 32 tcgen05.alloc accepts
-static int tmem_stack_cols(int warps, int depth) {
-    const int need = ((warps + 3) / 4) * depth * 8;
+static int tmem_stack_cols(int warps, int depth, int K = 8) {
+    const int need = ((warps + 3) / 4) * depth * K;
     int cols = 32;
     while (cols < need) cols <<= 1;
     return cols;
@@ -581,6 +616,12 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         a.sched = sched0 + t;                                  // one ticket counter per launch (64 zeroed by lower_kernel)
         const size_t data = per_dp * a.NP;
         int warps = 8;
+        if constexpr (K == 16) {
+            // one CTA per SM: as many warps as registers (~100 per thread) and the 512 columns allow - five per lane
+            // quarter for stacks of up to 6 slots
+            const int per_quarter = 512 / (depth * 16) < 5 ? 512 / (depth * 16) : 5;
+            warps = 4 * (per_quarter < 1 ? 1 : per_quarter);
+        }
         while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
         size_t smem = data + warps * per_warp();
         EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -591,7 +632,7 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
             // The occupancy API answers 1 CTA/SM for a kernel that allocates tensor memory; the real limits are
             // registers, shared memory and the 512 columns (every resident CTA holds its columns until it exits,
             // and tcgen05.alloc blocks when they run out - CTAs beyond `fit` would only wait).
-            a.tmem_cols = tmem_stack_cols(warps, depth);
+            a.tmem_cols = tmem_stack_cols(warps, depth, K);
             const int fit = 512 / a.tmem_cols;
             cudaFuncAttributes fa;
             EVOGP_CUDA(cudaFuncGetAttributes(&fa, kern));
@@ -614,17 +655,38 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     return EVOGP_OK;
 }
 
+// Which single-output replay kernel serves a launch: 16 or 8 datapoints per lane with the operand stack in tensor
+// memory, or the shared-memory-stack kernels (K = 8 / 4 / 1).  Decided before the lowering pass because K = 16
+// wants split-mode programs (lower.cuh).
+struct ReplayChoice {
+    int K;
+    bool tmem;
+};
+static ReplayChoice choose_replay(bool multi, int mode, int N, int depth) {
+    ReplayChoice c{1, false};
+    if (mode == MODE_ROWWISE) return c;
+    c.K = choose_k(N);
+    if (multi || c.K != 8 || !g_use_tmem_stack) return c;
+    // tensor-memory stack while two warps per lane quarter fit the columns (depth <= 8, i.e. max_tree_len <= 256);
+    // 16 datapoints per lane when that does not waste passes on padding (cost model of choose_k;
+    // EVOGP_REPLAY_K=8|16 overrides)
+    const int d = depth > 0 ? depth : 1;
+    const double c8 = (double)((N + 255) / 256) * (14.0 + 16.0), c16 = (double)((N + 511) / 512) * (14.0 + 32.0);
+    const bool want16 = g_force_k ? g_force_k == 16 : c16 < c8;
+    if (want16 && tmem_stack_cols(8, d, 16) <= 256) { c.K = 16; c.tmem = true; }
+    else if (tmem_stack_cols(8, d, 8) <= 128) c.tmem = true;
+    return c;
+}
+
 template <bool MULTI>
-static int launch_replay(const ReplayArgs &a, int depth, cudaStream_t st) {
+static int launch_replay(const ReplayArgs &a, int depth, ReplayChoice c, cudaStream_t st) {
     if (a.mode == MODE_ROWWISE) return launch_replay_t<1, MULTI, true>(a, depth, st);
-    switch (choose_k(a.N)) {
-    case 8:
-        if constexpr (!MULTI) {
-            // operand stack in tensor memory while two warps per lane quarter fit 128 columns (depth <= 8, i.e.
-            // max_tree_len <= 256); deeper stacks keep the shared-memory kernel
-            if (tmem_stack_cols(8, depth > 0 ? depth : 1) <= 128 && g_use_tmem_stack) return launch_replay_t<8, false, false, true>(a, depth, st);
-        }
-        return launch_replay_t<8, MULTI, false>(a, depth, st);
+    if constexpr (!MULTI) {
+        if (c.K == 16) return launch_replay_t<16, false, false, true>(a, depth, st);
+        if (c.K == 8 && c.tmem) return launch_replay_t<8, false, false, true>(a, depth, st);
+    }
+    switch (c.K) {
+    case 8: return launch_replay_t<8, MULTI, false>(a, depth, st);
     case 4: return launch_replay_t<4, MULTI, false>(a, depth, st);
     default: return launch_replay_t<1, MULTI, false>(a, depth, st);
     }
@@ -651,14 +713,15 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
-    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, st)
-               : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, st);
+    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth);
+    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, st)
+               : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16, st);
     if (rc) return rc;
     ReplayArgs a;
     a.prog = w.prog; a.sched = w.sched; a.X = X; a.labels = labels; a.out = out;
     a.P = (int)P; a.Lp = prog_pitch(L); a.N = (int)N; a.V = (int)V; a.O = (int)O;
     a.NP = 0; a.npass = 0; a.depth = depth; a.mode = mode;
-    return multi ? launch_replay<true>(a, depth, st) : launch_replay<false>(a, depth, st);
+    return multi ? launch_replay<true>(a, depth, choice, st) : launch_replay<false>(a, depth, choice, st);
 }
 
 }  // namespace evogp

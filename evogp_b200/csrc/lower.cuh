@@ -313,9 +313,13 @@ __host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
 }
 
 // Single-output rows.  Returns the operand-stack height the program needs, or -1 for a malformed row.
+template <bool split>
 __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
                                                  int len, int L, int Lp, int V, int depth_budget, uint2 *out,
                                                  LowerScratch k, bool have_sizes) {
+    // split: operators on leaves only are emitted as LOAD + acc-form instead of the fresh-value forms
+    // (UV/UK/VV/VK/KV), so programs use 6 operand forms per operator instead of 9 - the K = 16 replay kernel
+    // keeps only those laid out (its bodies are twice as long; the instruction cache is its limit)
     if (!stage_rows(ln, val, typ, size, len, L, k, have_sizes)) {
         emit_nan(ln, out, Lp);
         return -1;
@@ -342,9 +346,9 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
             if ((int)k.s[i] != tot || i + tot > len) mine = true;
             int m = 0;
             if (!mine) {
-                if (ar == 1) m = 1;
-                else if (ar == 2)    // two constants: LOAD + AK
-                    m = (!is_func(c[0]) && !is_func(c[1]) && is_const(c[0]) && is_const(c[1])) ? 2 : 1;
+                if (ar == 1) m = (split && !is_func(c[0])) ? 2 : 1;
+                else if (ar == 2)    // two constants (or split): LOAD + AK / AV
+                    m = (!is_func(c[0]) && !is_func(c[1]) && (split || (is_const(c[0]) && is_const(c[1])))) ? 2 : 1;
                 else if (ar == 3)    // every leaf child is a LOAD
                     m = 1 + (!is_func(c[0])) + (!is_func(c[1])) + (!is_func(c[2]));
             }
@@ -445,13 +449,16 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
         if (ar == 1) {
             const int u = unary_slot(func), c = i + 1;
             if (is_func(c)) out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
-            else out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u), leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
+            else if (split) {
+                out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
+                out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
+            } else out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u), leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
         } else if (ar == 2) {
             const int b = binary_slot(func), x = i + 1, y = x + k.s[x];
             const bool cx = is_func(x), cy = is_func(y);
             if (!cx && !cy) {
                 const Leaf lx = leaf_of(k.t[x], bits_f32(k.v[x]), V), ly = leaf_of(k.t[y], bits_f32(k.v[y]), V);
-                if (lx.is_const && ly.is_const) {          // two constants: load the first, then acc (op) const
+                if (split || (lx.is_const && ly.is_const)) {   // (two constants:) load the first, then acc (op) second
                     out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, lx, live_push);
                     out[st + 1] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), ly, 0);
                 } else if (!lx.is_const && !ly.is_const) {
@@ -556,12 +563,12 @@ __host__ __device__ inline int lower_tree_multi(Lanes ln, const float *val, cons
     return 0;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool SPLIT = false>
 __host__ __device__ inline int lower_tree(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
                                           int L, int Lp, int V, int O, int depth_budget, uint2 *out, LowerScratch k,
                                           bool have_sizes = true) {
     if (MULTI) return lower_tree_multi(ln, val, typ, size, len, L, Lp, V, O, out, k, have_sizes);
-    return lower_tree_single(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes);
+    return lower_tree_single<SPLIT>(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes);
 }
 
 #ifdef __CUDACC__
@@ -575,7 +582,8 @@ struct LowerArgs {
 };
 
 // one warp per tree, grid-stride over the population
-template <bool MULTI>
+// SPLIT (single-output only): LOAD + acc-form for operators on leaves (see lower_tree_single)
+template <bool MULTI, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
     extern __shared__ __align__(16) unsigned char lower_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
         // rows_have_sizes == 0 (host path uploads one length per tree): sizes are recomputed from the arities
         const int16_t *srow = g.rows_have_sizes ? g.size + (size_t)n * g.L : nullptr;
         const int len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
-        lower_tree<MULTI>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
+        lower_tree<MULTI, SPLIT>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
                           g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0);
         __syncwarp();
     }

@@ -19,13 +19,14 @@ using namespace evogp;
 
 template <bool MULTI>
 static int run_row(const float *val, const int16_t *typ, const int16_t *size, int len, int L, int V, int O, const float *X,
-                   int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out) {
+                   int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out, bool split = false) {
     const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
     std::vector<unsigned char> mem(lower_scratch_bytes(L) + 64);
     const LowerScratch scratch = carve_scratch(mem.data(), L);
     const int budget = stack_depth_bound(L);
-    const int need = lower_tree<MULTI>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch);
+    const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch)
+                           : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch);
     *need_out = need;
     int ninstr = 0;
     while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
@@ -129,12 +130,14 @@ extern "C" int harness_batch_forward(int P, int N, int L, int V, int O, const fl
     for (int n = 0; n < P; ++n) {
         const int len = size[(size_t)n * L];
         int rc;
-        // use_sizes: 1 = pass the subtree_size row (verified / trusted), 0 = pass none (recomputed from arities)
-        const int16_t *srow = use_sizes ? size + (size_t)n * L : nullptr;
+        // use_sizes bit 0: 1 = pass the subtree_size row (verified / trusted), 0 = pass none (recomputed from arities);
+        // bit 1: lower in split mode (LOAD + acc-form instead of the fresh-value forms)
+        const int16_t *srow = (use_sizes & 1) ? size + (size_t)n * L : nullptr;
+        const bool split = (use_sizes & 2) != 0;
         if (O > 1) rc = run_row<true>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n);
+                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split);
         else rc = run_row<false>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n);
+                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split);
         if (rc) return rc * 1000000 - n;
     }
     return 0;

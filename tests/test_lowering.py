@@ -63,6 +63,11 @@ def test_lowered_program_equals_stack_machine(harness, orc, funcs, L, layers, V)
     assert (need >= 0).all() and (maxsp <= need).all()
     bound = harness.harness_depth_bound(L)
     assert need.max() <= bound
+    # split mode (what the K = 16 replay kernel is fed): LOAD + acc-form instead of the fresh-value forms
+    got2, need2, ninstr2, maxsp2 = run(harness, v, t, s, X, 1, use_sizes=3)
+    assert same(got2, want)
+    assert (ninstr2 <= lens).all() and (ninstr2 >= ninstr).all()
+    assert (need2 == need).all() and (maxsp2 <= need2).all()
 
 
 def test_multi_output_programs(harness, orc):
