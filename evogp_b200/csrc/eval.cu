@@ -43,7 +43,8 @@ struct ReplayArgs {
     int P, Lp, N, V, O;
     int NP;                 // N rounded up to a whole number of passes
     int npass, depth, mode;
-    int smem_depth;         // operand-stack slots per warp kept in shared memory (0 when the stack is in tensor memory)
+    int smem_depth;         // operand-stack slots per warp kept in shared memory
+    int tmem_slots;         // TSTK: slots [0, tmem_slots) live in tensor memory, the deeper ones in shared memory
     int tmem_cols;          // TSTK: tensor-memory columns the CTA allocates (power of two >= 32)
     // datapoint tiling (dataset larger than the shared-memory staging area): this launch covers datapoints
     // [d_base, d_base + N) of N_total; loss modes carry the running sum in out[] between launches
@@ -141,7 +142,7 @@ __device__ __forceinline__ int dp_index(int lane, int k) {
 
 // TSTK: the operand stack lives in tensor memory instead of shared memory (K == 8, single-output only)
 template <int K, bool MULTI, bool ROWWISE, bool TSTK = false>
-__global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K == 8) ? 4 : 2)) replay_kernel(ReplayArgs g) {
+__global__ void __launch_bounds__(K == 16 ? 768 : 256, K == 16 ? 1 : ((TSTK && K == 8) ? 4 : 2)) replay_kernel(ReplayArgs g) {
     static_assert(!TSTK || ((K == 8 || K == 16) && !MULTI && !ROWWISE), "tensor-memory stack: K = 8 / 16 single-output only");
     static_assert(K != 16 || TSTK, "K = 16 exists only with the tensor-memory stack");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K
     __syncthreads();
     if constexpr (TSTK) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.depth * (uint32_t)K;
+        tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.tmem_slots * (uint32_t)K;
     }
 
     const uint32_t row_bytes = (uint32_t)g.Lp * 8u;
@@ -241,24 +242,27 @@ __global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K
                 }
             };
 
-            float acc[K], bankB[K], bankC[K];   // accumulator; operand-stack slots 0 and 1 (registers)
-            FOR_K { acc[k] = 0.0f; bankB[k] = 0.0f; bankC[k] = 0.0f; }
+            float acc[K];
+            FOR_K acc[k] = 0.0f;
             if constexpr (MULTI) {
                 for (int o = 0; o < g.O; ++o) st_vec<K>(outs + o * SLOT + lane_off, acc);
             }
             int pc = 0;
-            // operand-stack slots are static (program.cuh): 0 -> bankB, 1 -> bankC, s >= 2 -> shared memory
+            // operand-stack slots are static (program.cuh).  TSTK: slots < tmem_slots in tensor memory, deeper ones
+            // (reached only through the deep opcodes, i.e. through this generic path) in shared memory
             auto slot_store = [&](int slot) {
-                if constexpr (TSTK) { tmem_store_slot<K>(tstack + (uint32_t)slot * (uint32_t)K, acc); return; }
-                if (slot == 0 && kRegSlots > 0) { FOR_K bankB[k] = acc[k]; }
-                else if (slot == 1 && kRegSlots > 1) { FOR_K bankC[k] = acc[k]; }
-                else st_vec<K>(stack + (slot - kRegSlots) * SLOT + lane_off, acc);
+                if constexpr (TSTK) {
+                    if (slot < g.tmem_slots) { tmem_store_slot<K>(tstack + (uint32_t)slot * (uint32_t)K, acc); return; }
+                    slot -= g.tmem_slots;
+                }
+                st_vec<K>(stack + slot * SLOT + lane_off, acc);
             };
             auto slot_load = [&](float(&d)[K], int slot) {
-                if constexpr (TSTK) { tmem_load_slot<K>(d, tstack + (uint32_t)slot * (uint32_t)K); return; }
-                if (slot == 0 && kRegSlots > 0) { FOR_K d[k] = bankB[k]; }
-                else if (slot == 1 && kRegSlots > 1) { FOR_K d[k] = bankC[k]; }
-                else ld_vec<K>(d, stack + (slot - kRegSlots) * SLOT + lane_off);
+                if constexpr (TSTK) {
+                    if (slot < g.tmem_slots) { tmem_load_slot<K>(d, tstack + (uint32_t)slot * (uint32_t)K); return; }
+                    slot -= g.tmem_slots;
+                }
+                ld_vec<K>(d, stack + slot * SLOT + lane_off);
             };
 
             // ---- generic interpreter: one instruction per call; two stages (operands by form,
@@ -291,8 +295,8 @@ __global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K
                     }
                     switch (form) {
                     case FM_MISC:
-                        if (code == C_LOAD_V) { fetch_var(acc, ia); return false; }
-                        if (code == C_LOAD_K) { FOR_K acc[k] = cst; return false; }
+                        if (code == C_LOAD_V || code == C_LOAD_V_DEEP) { fetch_var(acc, ia); return false; }
+                        if (code == C_LOAD_K || code == C_LOAD_K_DEEP) { FOR_K acc[k] = cst; return false; }
                         if (code == C_IF) {   // forward.cu:223
                             float t1[K], t2[K];
                             slot_load(t1, (int)ib + 1);   // newer of the two saved values
@@ -321,12 +325,8 @@ __global__ void __launch_bounds__(K == 16 ? 640 : 256, K == 16 ? 1 : ((TSTK && K
                     case FM_VV: fetch_var(x, ia); fetch_var(y, ib); break;
                     case FM_VK: fetch_var(x, ia); FOR_K y[k] = cst; break;
                     case FM_KV: FOR_K x[k] = cst; fetch_var(y, ia); break;
-                    case FM_SA: slot_load(x, (int)ia + kRegSlots); FOR_K y[k] = acc[k]; break;
-                    case FM_AS: FOR_K x[k] = acc[k]; slot_load(y, (int)ia + kRegSlots); break;
-                    case FM_BA: FOR_K { x[k] = bankB[k]; y[k] = acc[k]; } break;
-                    case FM_AB: FOR_K { x[k] = acc[k]; y[k] = bankB[k]; } break;
-                    case FM_CA: FOR_K { x[k] = bankC[k]; y[k] = acc[k]; } break;
-                    case FM_AC: FOR_K { x[k] = acc[k]; y[k] = bankC[k]; } break;
+                    case FM_SA: case FM_DA: slot_load(x, (int)ia); FOR_K y[k] = acc[k]; break;
+                    case FM_AS: case FM_AD: FOR_K x[k] = acc[k]; slot_load(y, (int)ia); break;
                     default: FOR_K { x[k] = 0.0f; y[k] = 0.0f; } break;
                     }
                     if (form <= FM_UK) {
@@ -506,6 +506,8 @@ static Workspace carve(void *ws, unsigned P, unsigned L) {
     return w;
 }
 
+constexpr int kTmemSlots16 = 4;   // K = 16: operand-stack slots kept in tensor memory (deeper ones: shared memory)
+
 template <bool MULTI, bool SPLIT>
 static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
                           const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
@@ -525,6 +527,7 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
     a.rows_have_sizes = len_stride != 1;
+    a.deep_from = SPLIT ? kTmemSlots16 : kNoDeepSlots;
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
     static int per_sm_cached = 0;
@@ -568,8 +571,8 @@ static int choose_k(int N) {
 
 // tensor-memory columns a CTA of `warps` warps needs for operand stacks of `depth` slots (8 columns per slot; the
 // warps of one lane quarter share the columns), as the power of two >= 32 tcgen05.alloc accepts
-static int tmem_stack_cols(int warps, int depth, int K = 8) {
-    const int need = ((warps + 3) / 4) * depth * K;
+static int tmem_stack_cols(int warps, int slots, int K = 8) {
+    const int need = ((warps + 3) / 4) * slots * K;
     int cols = 32;
     while (cols < need) cols <<= 1;
     return cols;
@@ -581,9 +584,12 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     const int SLOT = K * 32;
     a.npass = ROWWISE ? 1 : (a.N + SLOT - 1) / SLOT;
     a.NP = a.npass * SLOT;
-    a.depth = MULTI ? 1 : (depth > kRegSlots ? depth - kRegSlots : 1);   // multi-output programs use no operand stack
+    a.depth = MULTI ? 1 : (depth > 0 ? depth : 1);   // multi-output programs use no operand stack
     depth = a.depth;
-    a.smem_depth = TSTK ? 0 : depth;
+    // TSTK: K = 8 keeps the whole stack in tensor memory (the launcher only picks it for depth <= 8); K = 16 keeps
+    // the first kTmemSlots16 slots there and the deeper, rarely reached ones in shared memory (deep opcodes)
+    a.tmem_slots = TSTK ? (K == 16 ? (depth < kTmemSlots16 ? depth : kTmemSlots16) : depth) : 0;
+    a.smem_depth = depth - a.tmem_slots;
     a.tmem_cols = 0;
     auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)a.smem_depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
     // the dataset slice a launch stages: all of it when it fits next to >= 4 warps, else whole passes of it
@@ -617,10 +623,9 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         const size_t data = per_dp * a.NP;
         int warps = 8;
         if constexpr (K == 16) {
-            // one CTA per SM: as many warps as registers (~100 per thread) and the 512 columns allow - five per lane
-            // quarter for stacks of up to 6 slots
-            const int per_quarter = 512 / (depth * 16) < 5 ? 512 / (depth * 16) : 5;
-            warps = 4 * (per_quarter < 1 ? 1 : per_quarter);
+            // one CTA per SM: as many warps as the registers (80 per thread at 768 threads) allow; their
+            // kTmemSlots16 slots of 16 columns fit the 512 columns with room to spare
+            warps = 24;
         }
         while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
         size_t smem = data + warps * per_warp();
@@ -632,7 +637,7 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
             // The occupancy API answers 1 CTA/SM for a kernel that allocates tensor memory; the real limits are
             // registers, shared memory and the 512 columns (every resident CTA holds its columns until it exits,
             // and tcgen05.alloc blocks when they run out - CTAs beyond `fit` would only wait).
-            a.tmem_cols = tmem_stack_cols(warps, depth, K);
+            a.tmem_cols = tmem_stack_cols(warps, a.tmem_slots, K);
             const int fit = 512 / a.tmem_cols;
             cudaFuncAttributes fa;
             EVOGP_CUDA(cudaFuncGetAttributes(&fa, kern));
@@ -673,7 +678,7 @@ static ReplayChoice choose_replay(bool multi, int mode, int N, int depth) {
     const int d = depth > 0 ? depth : 1;
     const double c8 = (double)((N + 255) / 256) * (14.0 + 16.0), c16 = (double)((N + 511) / 512) * (14.0 + 32.0);
     const bool want16 = g_force_k ? g_force_k == 16 : c16 < c8;
-    if (want16 && tmem_stack_cols(8, d, 16) <= 256) { c.K = 16; c.tmem = true; }
+    if (want16) { c.K = 16; c.tmem = true; }
     else if (tmem_stack_cols(8, d, 8) <= 128) c.tmem = true;
     return c;
 }

@@ -316,7 +316,7 @@ __host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
 template <bool split>
 __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
                                                  int len, int L, int Lp, int V, int depth_budget, uint2 *out,
-                                                 LowerScratch k, bool have_sizes) {
+                                                 LowerScratch k, bool have_sizes, int deep_from) {
     // split: operators on leaves only are emitted as LOAD + acc-form instead of the fresh-value forms
     // (UV/UK/VV/VK/KV), so programs use 6 operand forms per operator instead of 9 - the K = 16 replay kernel
     // keeps only those laid out (its bodies are twice as long; the instruction cache is its limit)
@@ -438,10 +438,12 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
         const int st = d & 0xFFFF;
         const uint32_t live = pending ? 1u : 0u, height = pending ? pending - 1 : 0u;
         const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
+        const bool deep_push = live && (int)height >= deep_from;                // (only reachable in split mode)
+        const int ld_v = deep_push ? C_LOAD_V_DEEP : C_LOAD_V, ld_k = deep_push ? C_LOAD_K_DEEP : C_LOAD_K;
         const uint32_t height_in = height + live;
         if (live) my_max = my_max > (int)height + 1 ? my_max : (int)height + 1;
         if (ar == 0) {                            // leaf child of a ternary node: produced by a LOAD
-            out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[i], bits_f32(k.v[i]), V), live_push);
+            out[st] = leaf_instr(ld_v, ld_k, leaf_of(k.t[i], bits_f32(k.v[i]), V), live_push);
             continue;
         }
         const int own = st + ni(i) - 1;
@@ -450,7 +452,7 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
             const int u = unary_slot(func), c = i + 1;
             if (is_func(c)) out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
             else if (split) {
-                out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
+                out[st] = leaf_instr(ld_v, ld_k, leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
                 out[own] = mk2((uint32_t)opcode(FM_UA, u), 0);
             } else out[own] = leaf_instr(opcode(FM_UV, u), opcode(FM_UK, u), leaf_of(k.t[c], bits_f32(k.v[c]), V), live_push);
         } else if (ar == 2) {
@@ -459,7 +461,7 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
             if (!cx && !cy) {
                 const Leaf lx = leaf_of(k.t[x], bits_f32(k.v[x]), V), ly = leaf_of(k.t[y], bits_f32(k.v[y]), V);
                 if (split || (lx.is_const && ly.is_const)) {   // (two constants:) load the first, then acc (op) second
-                    out[st] = leaf_instr(C_LOAD_V, C_LOAD_K, lx, live_push);
+                    out[st] = leaf_instr(ld_v, ld_k, lx, live_push);
                     out[st + 1] = leaf_instr(opcode(FM_AV, b), opcode(FM_AK, b), ly, 0);
                 } else if (!lx.is_const && !ly.is_const) {
                     out[own] = mk2((uint32_t)opcode(FM_VV, b) | live_push | (lx.bits << I_IDXA_SHIFT) | (ly.bits << I_IDXB_SHIFT), 0);
@@ -471,12 +473,9 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
             } else if (cx && cy) {
                 const bool x_first = (k.q[x] & 3) == 0;
                 // the first child's value was saved into slot `height_in` by the second child's first instruction
-                int form;
-                uint32_t slot_arg = 0;
-                if (height_in == 0 && kRegSlots > 0) form = x_first ? FM_BA : FM_AB;
-                else if (height_in == 1 && kRegSlots > 1) form = x_first ? FM_CA : FM_AC;
-                else { form = x_first ? FM_SA : FM_AS; slot_arg = (height_in - kRegSlots) << I_IDXA_SHIFT; }
-                out[own] = mk2((uint32_t)opcode(form, b) | slot_arg, 0);
+                const bool deep = (int)height_in >= deep_from;
+                const int form = x_first ? (deep ? FM_DA : FM_SA) : (deep ? FM_AD : FM_AS);
+                out[own] = mk2((uint32_t)opcode(form, b) | (height_in << I_IDXA_SHIFT), 0);
                 my_max = my_max > (int)height_in + 1 ? my_max : (int)height_in + 1;
             } else {
                 const int lf = cx ? y : x;
@@ -566,9 +565,10 @@ __host__ __device__ inline int lower_tree_multi(Lanes ln, const float *val, cons
 template <bool MULTI, bool SPLIT = false>
 __host__ __device__ inline int lower_tree(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
                                           int L, int Lp, int V, int O, int depth_budget, uint2 *out, LowerScratch k,
-                                          bool have_sizes = true) {
+                                          bool have_sizes = true, int deep_from = kNoDeepSlots) {
     if (MULTI) return lower_tree_multi(ln, val, typ, size, len, L, Lp, V, O, out, k, have_sizes);
-    return lower_tree_single<SPLIT>(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes);
+    return lower_tree_single<SPLIT>(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes,
+                                    SPLIT ? deep_from : kNoDeepSlots);   // deep pushes exist only on LOADs (split mode)
 }
 
 #ifdef __CUDACC__
@@ -579,6 +579,7 @@ struct LowerArgs {
     uint2 *prog;              // [P][Lp]
     unsigned *sched;          // 64 scheduler words, zeroed here (the replay kernel runs after this one)
     int P, L, Lp, V, O, depth_budget, rows_have_sizes;
+    int deep_from;            // SPLIT: slots >= deep_from are addressed with the deep opcodes (program.cuh); else kNoDeepSlots
 };
 
 // one warp per tree, grid-stride over the population
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
         const int16_t *srow = g.rows_have_sizes ? g.size + (size_t)n * g.L : nullptr;
         const int len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
         lower_tree<MULTI, SPLIT>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
-                          g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0);
+                          g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0, g.deep_from);
         __syncwarp();
     }
 }

@@ -27,16 +27,20 @@ namespace evogp {
 //                          (LOAD_*, UV/UK, VV, VK, KV).  Multi-output programs never push; there
 //                          bit 9 is OUT (add the result to outs[idxB]) and bits 10-12 are the
 //                          constant flags of C_IF3.
-//          [22:13] idxA    variable index of the (first) variable operand; SA/AS: stack slot - 2;
+//          [22:13] idxA    variable index of the (first) variable operand; SA/AS/DA/AD: stack slot;
 //                          C_IF: operand permutation
 //          [31:23] idxB    variable index of the second variable operand (VV); output index when
 //                          OUT (0x1FF: out of range, result dropped); C_IF: lower of its two slots
 //   constant       the constant operand of a *K* form, bit-cast
 // Operand kinds are part of the opcode, so the replay loop never tests a flag to find an operand:
-//   A accumulator, V variable (dataset column), K constant, B / C operand-stack slots 0 / 1 (held
-//   in registers), S operand-stack slot >= 2 (shared memory).  Slot numbers are static: sibling
-//   order is fixed by the lowering pass, so the stack height at every push and pop is known there
-//   and the replay loop keeps no stack pointer.
+//   A accumulator, V variable (dataset column), K constant, S operand-stack slot, D "deep" operand-stack
+//   slot.  Slot numbers are static: sibling order is fixed by the lowering pass, so the stack height at
+//   every push and pop is known there and the replay loop keeps no stack pointer.
+//   Deep slots: a kernel that keeps only the first T slots in its fast storage (tensor memory) asks the
+//   lowering pass (deep_from = T) to mark every access to a slot >= T in the opcode - pushes as
+//   C_LOAD_*_DEEP, pops as the DA / AD forms - so its hot bodies never test the slot number; those
+//   opcodes take the generic path, which keeps slots >= T in shared memory.  Programs for kernels with
+//   one stack medium (deep_from = none) never contain them.
 // ---------------------------------------------------------------------------
 constexpr uint32_t I_CODE_MASK = 0x1FFu;
 constexpr int I_PUSH_SHIFT = 9;
@@ -45,10 +49,9 @@ constexpr uint32_t I_OUT = 1u << 9;                                             
 constexpr uint32_t I_IF3_ACONST = 1u << 10, I_IF3_BCONST = 1u << 11, I_IF3_CCONST = 1u << 12;
 constexpr int I_IDXA_SHIFT = 13, I_IDXB_SHIFT = 23;
 constexpr uint32_t I_IDXA_MASK = 0x3FFu, I_IDXB_MASK = 0x1FFu;
-// operand-stack slots held in registers (banks B, C).  Measured on B200 (profiles/r1_replay_v3_regbanks.txt):
-// 2 banks cut shared-memory wavefronts by 45 % but cost 25 registers (occupancy 24 -> 16 warps/SM), extra
-// MOV/dispatch work per save and a larger instruction footprint — net slower (479 us vs 309 us) — so 0 for now.
-constexpr int kRegSlots = 0;
+// (Operand-stack slots held in registers were measured and rejected: profiles/r1_replay_v3_regbanks.txt - 45 %
+// fewer shared-memory wavefronts but 25 more registers and MOV work per save, 479 us vs 309 us.)
+constexpr int kNoDeepSlots = 255;   // deep_from value meaning "every slot is an ordinary slot"
 
 constexpr int NUM_U = 16;  // 15 unary functions (ids 14..28) + "unknown id -> 0"
 constexpr int NUM_B = 14;  // 13 binary functions (ids 1..13) + "unknown id -> 0"
@@ -67,13 +70,11 @@ enum : int {
     FM_VV = 8,   // acc = b(var A, var B)
     FM_VK = 9,   // acc = b(var A, const)
     FM_KV = 10,  // acc = b(const, var A)
-    FM_SA = 11,  // acc = b(slot[idxA + 2], acc)
-    FM_AS = 12,  // acc = b(acc, slot[idxA + 2])
-    FM_BA = 13,  // acc = b(B, acc)      slot 0
-    FM_AB = 14,  // acc = b(acc, B)
-    FM_CA = 15,  // acc = b(C, acc)      slot 1
-    FM_AC = 16,  // acc = b(acc, C)
-    FM_COUNT = 17
+    FM_SA = 11,  // acc = b(slot[idxA], acc)
+    FM_AS = 12,  // acc = b(acc, slot[idxA])
+    FM_DA = 13,  // acc = b(slot[idxA], acc)      idxA >= deep_from
+    FM_AD = 14,  // acc = b(acc, slot[idxA])
+    FM_COUNT = 15
 };
 // FM_MISC opcodes
 enum : int {
@@ -83,6 +84,8 @@ enum : int {
     C_NAN = 3,     // malformed row: result NaN
     C_IF = 4,      // acc = a > 0 ? b : c; operands are acc / slot idxB+1 / slot idxB per idxA
     C_IF3 = 5,     // multi-output only, 2 slots {hdr, a}{b, c}: r = a > 0 ? b : c on three leaf operands
+    C_LOAD_V_DEEP = 6,   // C_LOAD_V / C_LOAD_K whose PUSH targets a deep slot
+    C_LOAD_K_DEEP = 7,
     C_COUNT = FM_COUNT * 16
 };
 __host__ __device__ inline int opcode(int form, int op) { return form * 16 + op; }

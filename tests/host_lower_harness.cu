@@ -19,14 +19,16 @@ using namespace evogp;
 
 template <bool MULTI>
 static int run_row(const float *val, const int16_t *typ, const int16_t *size, int len, int L, int V, int O, const float *X,
-                   int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out, bool split = false) {
+                   int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out, bool split = false,
+                   int deep_from = kNoDeepSlots) {
     const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
     std::vector<unsigned char> mem(lower_scratch_bytes(L) + 64);
     const LowerScratch scratch = carve_scratch(mem.data(), L);
     const int budget = stack_depth_bound(L);
-    const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch)
+    const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from)
                            : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch);
+    if (!split) deep_from = kNoDeepSlots;
     *need_out = need;
     int ninstr = 0;
     while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
@@ -67,15 +69,18 @@ static int run_row(const float *val, const int16_t *typ, const int16_t *size, in
             if (!MULTI) {
                 const int push = (w & I_PUSH_MASK) >> I_PUSH_SHIFT;
                 if (push) {
-                    if (!(code == C_LOAD_V || code == C_LOAD_K || form == FM_UV || form == FM_UK || form == FM_VV ||
+                    const bool deep_load = code == C_LOAD_V_DEEP || code == C_LOAD_K_DEEP;
+                    if (!(code == C_LOAD_V || code == C_LOAD_K || deep_load || form == FM_UV || form == FM_UK || form == FM_VV ||
                           form == FM_VK || form == FM_KV)) return -6;   // PUSH only on fresh-value instructions
+                    if (deep_load != (push - 1 >= deep_from)) return -8;   // deep slots are marked in the opcode, and only they
                     if (push - 1 != height || filled[push - 1]) return -7;   // static slot == dynamic height
                     stack[push - 1] = acc; filled[push - 1] = 1; ++height;
                     if (height > maxsp) maxsp = height;
                 }
             }
-            if (code == C_LOAD_V) { acc = var(ia); continue; }
-            if (code == C_LOAD_K) { acc = cst; continue; }
+            if ((code == C_LOAD_V_DEEP || code == C_LOAD_K_DEEP) && !((w & I_PUSH_MASK) >> I_PUSH_SHIFT)) return -8;
+            if (code == C_LOAD_V || code == C_LOAD_V_DEEP) { acc = var(ia); continue; }
+            if (code == C_LOAD_K || code == C_LOAD_K_DEEP) { acc = cst; continue; }
             if (code == C_NAN) { acc = NAN; for (int o = 0; o < O; ++o) outs[o] = NAN; continue; }
             float r;
             if (code == C_IF) {
@@ -87,7 +92,7 @@ static int run_row(const float *val, const int16_t *typ, const int16_t *size, in
             } else if (form >= FM_UA && form <= FM_UK) {
                 const float a = form == FM_UA ? acc : (form == FM_UV ? var(ia) : cst);
                 r = oracle_apply_unary(op + F_SIN, a);
-            } else if (form >= FM_AV && form <= FM_AC) {
+            } else if (form >= FM_AV && form <= FM_AD) {
                 float a, b, s;
                 switch (form) {
                 case FM_AV: a = acc; b = var(ia); break;
@@ -97,12 +102,10 @@ static int run_row(const float *val, const int16_t *typ, const int16_t *size, in
                 case FM_VV: a = var(ia); b = var(ib); break;
                 case FM_VK: a = var(ia); b = cst; break;
                 case FM_KV: a = cst; b = var(ia); break;
-                case FM_SA: if (!pop((int)ia + kRegSlots, s)) return -2; a = s; b = acc; break;
-                case FM_AS: if (!pop((int)ia + kRegSlots, s)) return -2; a = acc; b = s; break;
-                case FM_BA: if (kRegSlots < 1 || !pop(0, s)) return -2; a = s; b = acc; break;
-                case FM_AB: if (kRegSlots < 1 || !pop(0, s)) return -2; a = acc; b = s; break;
-                case FM_CA: if (kRegSlots < 2 || !pop(1, s)) return -2; a = s; b = acc; break;
-                default: if (kRegSlots < 2 || !pop(1, s)) return -2; a = acc; b = s; break;   // FM_AC
+                case FM_SA: if ((int)ia >= deep_from || !pop((int)ia, s)) return -2; a = s; b = acc; break;
+                case FM_AS: if ((int)ia >= deep_from || !pop((int)ia, s)) return -2; a = acc; b = s; break;
+                case FM_DA: if ((int)ia < deep_from || !pop((int)ia, s)) return -2; a = s; b = acc; break;
+                default: if ((int)ia < deep_from || !pop((int)ia, s)) return -2; a = acc; b = s; break;   // FM_AD
                 }
                 r = oracle_apply_binary(op + F_ADD, a, b);
             } else {
@@ -134,10 +137,11 @@ extern "C" int harness_batch_forward(int P, int N, int L, int V, int O, const fl
         // bit 1: lower in split mode (LOAD + acc-form instead of the fresh-value forms)
         const int16_t *srow = (use_sizes & 1) ? size + (size_t)n * L : nullptr;
         const bool split = (use_sizes & 2) != 0;
+        const int deep_from = (use_sizes & 4) ? 1 : kNoDeepSlots;   // bit 2: slots >= 1 are deep (exercises the deep opcodes)
         if (O > 1) rc = run_row<true>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split);
+                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from);
         else rc = run_row<false>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split);
+                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from);
         if (rc) return rc * 1000000 - n;
     }
     return 0;

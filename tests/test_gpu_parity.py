@@ -274,6 +274,53 @@ def test_degenerate_shapes(native, orc, kind, L):
     G.assert_close_fitness(got, want, rtol=1e-5, what=f"{kind} L={L}")
 
 
+def _ternary_forest(depth):
+    """IF of IFs of ... of leaves: the shape that needs the deepest operand stack per node (2 slots per level)."""
+    nodes = []
+
+    def rec(d):
+        nodes.append((4, 0.0))
+        if d == 0:
+            nodes.extend([(0, 0.0), (1, 1.0), (0, 1.0)])
+        else:
+            rec(d - 1); rec(d - 1); rec(d - 1)
+    rec(depth)
+    n = len(nodes)
+    L = n + (n & 1)
+    t = np.zeros((1, L), np.int16); v = np.zeros((1, L), np.float32); s = np.zeros((1, L), np.int16)
+    sizes = [0] * n
+    for i, (ty, val) in enumerate(nodes):
+        t[0, i], v[0, i] = ty, val
+    for i in range(n - 1, -1, -1):
+        ar = 0 if t[0, i] <= 1 else t[0, i] - 1
+        sz, c = 1, i + 1
+        for _ in range(ar):
+            sz += sizes[c]; c += sizes[c]
+        sizes[i] = sz
+    s[0, :n] = sizes
+    return v, t, s
+
+
+@pytest.mark.parametrize("N", [256, 1024])   # 8 datapoints per lane (whole stack in tensor memory while depth <= 8) and
+                                             # 16 (slots >= 4 in shared memory, reached through the deep opcodes)
+@pytest.mark.parametrize("shape", ["bushy127", "bushy1023", "ternary2", "ternary3"])
+def test_deep_operand_stacks(native, orc, shape, N):
+    if shape.startswith("bushy"):
+        v, t, s = _chain_forest(int(shape[5:]) + 1, "bushy")
+    else:
+        v, t, s = _ternary_forest(int(shape[7:]))
+    v, t, s = (np.repeat(a, 40, axis=0) for a in (v, t, s))      # several warps, same tree
+    orc.check_forest(v, t, s, input_len=2)
+    X, y = make_data(N, 2, seed=12)
+    want = orc.sr_fitness(v, t, s, X, y)
+    got = G.abi_sr_fitness(native, *G.to_dev(v, t, s, X, y))
+    torch.cuda.synchronize()
+    G.assert_close_fitness(got, want, rtol=1e-5, what=f"{shape} N={N}")
+    out = G.abi_batch_forward(native, *G.to_dev(v, t, s, X), 1).cpu().numpy().reshape(len(v), N)
+    ref_out = orc.batch_forward(v, t, s, X, 1).reshape(len(v), N)
+    assert np.allclose(out, ref_out, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
 def test_if_heavy_trees(native, orc):
     funcs = ["if", "if", "+", "<", "neg"]   # roulette normalises duplicates away; IF share is 1/4
     v, t, s = make_forest(orc, 4000, 121, 3, 1, ["if", "+", "<", "neg"], 5, keys=(13, 13), leaf_prob=0.1)

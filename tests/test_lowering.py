@@ -68,6 +68,9 @@ def test_lowered_program_equals_stack_machine(harness, orc, funcs, L, layers, V)
     assert same(got2, want)
     assert (ninstr2 <= lens).all() and (ninstr2 >= ninstr).all()
     assert (need2 == need).all() and (maxsp2 <= need2).all()
+    # ... with slots >= 1 marked deep (the harness checks that exactly those accesses use the deep opcodes)
+    got3, need3, ninstr3, _ = run(harness, v, t, s, X, 1, use_sizes=7)
+    assert same(got3, want) and (need3 == need).all() and (ninstr3 == ninstr2).all()
 
 
 def test_multi_output_programs(harness, orc):
