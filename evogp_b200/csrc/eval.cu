@@ -142,7 +142,7 @@ __device__ __forceinline__ int dp_index(int lane, int k) {
 
 // TSTK: the operand stack lives in tensor memory instead of shared memory (K == 8, single-output only)
 template <int K, bool MULTI, bool ROWWISE, bool TSTK = false>
-__global__ void __launch_bounds__(K == 16 ? 768 : 256, K == 16 ? 1 : ((TSTK && K == 8) ? 4 : 2)) replay_kernel(ReplayArgs g) {
+__global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && K == 8) ? 4 : 2)) replay_kernel(ReplayArgs g) {
     static_assert(!TSTK || ((K == 8 || K == 16) && !MULTI && !ROWWISE), "tensor-memory stack: K = 8 / 16 single-output only");
     static_assert(K != 16 || TSTK, "K = 16 exists only with the tensor-memory stack");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -625,7 +625,7 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         if constexpr (K == 16) {
             // one CTA per SM: as many warps as the registers (80 per thread at 768 threads) allow; their
             // kTmemSlots16 slots of 16 columns fit the 512 columns with room to spare
-            warps = 24;
+            warps = 32;
         }
         while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
         size_t smem = data + warps * per_warp();
