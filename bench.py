@@ -168,8 +168,6 @@ def run_ours(args):
         return fit
 
     abi = _native.abi()
-    ev_k0 = torch.cuda.Event(enable_timing=True); ev_k1 = torch.cuda.Event(enable_timing=True)
-    ev_k0.record(); ev_k1.record()    # materialise the handles
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
@@ -177,26 +175,31 @@ def run_ours(args):
         dist.barrier()
     sampler = ClockSampler(local); sampler.start()
     launches0 = _native.launch_count()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kern_ms = []
+    # Device-side timing, no host synchronisation inside the timed region: one event pair around the K steps gives the
+    # total, one pair per step (recorded inside the C ABI around the replay launch) the kernel's own duration.
     import ctypes
-    abi.evogp_eval_set_timing_events(ctypes.c_void_p(ev_k0.cuda_event), ctypes.c_void_p(ev_k1.cuda_event))
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:
+        a.record(); b.record()     # materialise the handles
+    ev_t0 = torch.cuda.Event(enable_timing=True); ev_t1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
+    ev_t0.record()
     for i in range(args.steps):
-        starts[i].record()
+        abi.evogp_eval_set_timing_events(ctypes.c_void_p(kev[i][0].cuda_event), ctypes.c_void_p(kev[i][1].cuda_event))
         step(i)
-        stops[i].record()
-        stops[i].synchronize()
-        kern_ms.append(ev_k0.elapsed_time(ev_k1))
+    ev_t1.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     abi.evogp_eval_set_timing_events(None, None)
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
     launches = _native.launch_count() - launches0
     sampler.stop_flag = True; sampler.join(timeout=2)
-    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    step_ms = [ev_t0.elapsed_time(ev_t1) / args.steps] * args.steps
+    total_ms = torch.tensor([ev_t0.elapsed_time(ev_t1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.barrier()
