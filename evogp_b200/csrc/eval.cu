@@ -474,6 +474,8 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
 static int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
 // EVOGP_TMEM_STACK=0 keeps the operand stack in shared memory (the A/B switch of profiles/; default on)
 static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_STACK"); return !(e && e[0] == '0'); }();
+// EVOGP_K16_SPLIT=1 feeds the K = 16 kernel split-mode programs (lower.cuh; the A/B switch of profiles/; default off)
+static const bool g_k16_split = []() { const char *e = getenv("EVOGP_K16_SPLIT"); return e && e[0] == '1'; }();
 static const int g_force_k = []() { const char *e = getenv("EVOGP_REPLAY_K"); return e ? atoi(e) : 0; }();
 // optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
@@ -510,7 +512,7 @@ constexpr int kTmemSlots16 = 4;   // K = 16: operand-stack slots kept in tensor 
 
 template <bool MULTI, bool SPLIT>
 static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
-                          const int16_t *type, const int16_t *size, int len_stride, int depth, cudaStream_t st) {
+                          const int16_t *type, const int16_t *size, int len_stride, int depth, int deep_from, cudaStream_t st) {
     auto kern = lower_kernel<MULTI, SPLIT>;
     // one warp per tree; per-warp scratch is 18 B per node slot (lower.cuh)
     const size_t per_warp = (lower_scratch_bytes((int)L) + 15) & ~(size_t)15;
@@ -527,7 +529,7 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
     a.rows_have_sizes = len_stride != 1;
-    a.deep_from = SPLIT ? kTmemSlots16 : kNoDeepSlots;
+    a.deep_from = deep_from;
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
     static int per_sm_cached = 0;
@@ -548,11 +550,12 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
 // split: single-output programs for the K = 16 replay kernel (LOAD + acc-form for operators on leaves)
 template <bool MULTI>
 static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
-                        const int16_t *type, const int16_t *size, int len_stride, int depth, bool split, cudaStream_t st) {
+                        const int16_t *type, const int16_t *size, int len_stride, int depth, bool split, int deep_from,
+                        cudaStream_t st) {
     if constexpr (!MULTI) {
-        if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, st);
+        if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
     }
-    return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, st);
+    return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
 }
 
 // cost model for choosing K: issue slots per datapoint ~ (dispatch overhead + K) / K, times padding waste
@@ -719,8 +722,9 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
     const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth);
-    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, st)
-               : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16, st);
+    const int deep_from = choice.K == 16 ? kTmemSlots16 : kNoDeepSlots;
+    rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, kNoDeepSlots, st)
+               : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16 && g_k16_split, deep_from, st);
     if (rc) return rc;
     ReplayArgs a;
     a.prog = w.prog; a.sched = w.sched; a.X = X; a.labels = labels; a.out = out;

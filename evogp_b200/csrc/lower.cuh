@@ -438,7 +438,7 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
         const int st = d & 0xFFFF;
         const uint32_t live = pending ? 1u : 0u, height = pending ? pending - 1 : 0u;
         const uint32_t live_push = live ? ((height + 1) << I_PUSH_SHIFT) : 0;   // a fresh value saves acc into slot `height`
-        const bool deep_push = live && (int)height >= deep_from;                // (only reachable in split mode)
+        const bool deep_push = live && (int)height >= deep_from;                // marks LOADs only; fresh forms carry the slot
         const int ld_v = deep_push ? C_LOAD_V_DEEP : C_LOAD_V, ld_k = deep_push ? C_LOAD_K_DEEP : C_LOAD_K;
         const uint32_t height_in = height + live;
         if (live) my_max = my_max > (int)height + 1 ? my_max : (int)height + 1;
@@ -568,7 +568,7 @@ __host__ __device__ inline int lower_tree(Lanes ln, const float *val, const int1
                                           bool have_sizes = true, int deep_from = kNoDeepSlots) {
     if (MULTI) return lower_tree_multi(ln, val, typ, size, len, L, Lp, V, O, out, k, have_sizes);
     return lower_tree_single<SPLIT>(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes,
-                                    SPLIT ? deep_from : kNoDeepSlots);   // deep pushes exist only on LOADs (split mode)
+                                    deep_from);
 }
 
 #ifdef __CUDACC__

@@ -27,8 +27,7 @@ static int run_row(const float *val, const int16_t *typ, const int16_t *size, in
     const LowerScratch scratch = carve_scratch(mem.data(), L);
     const int budget = stack_depth_bound(L);
     const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from)
-                           : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch);
-    if (!split) deep_from = kNoDeepSlots;
+                           : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from);
     *need_out = need;
     int ninstr = 0;
     while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
@@ -72,7 +71,7 @@ static int run_row(const float *val, const int16_t *typ, const int16_t *size, in
                     const bool deep_load = code == C_LOAD_V_DEEP || code == C_LOAD_K_DEEP;
                     if (!(code == C_LOAD_V || code == C_LOAD_K || deep_load || form == FM_UV || form == FM_UK || form == FM_VV ||
                           form == FM_VK || form == FM_KV)) return -6;   // PUSH only on fresh-value instructions
-                    if (deep_load != (push - 1 >= deep_from)) return -8;   // deep slots are marked in the opcode, and only they
+                    if ((code <= C_LOAD_K_DEEP) && deep_load != (push - 1 >= deep_from)) return -8;   // LOADs into deep slots are marked in the opcode
                     if (push - 1 != height || filled[push - 1]) return -7;   // static slot == dynamic height
                     stack[push - 1] = acc; filled[push - 1] = 1; ++height;
                     if (height > maxsp) maxsp = height;

@@ -71,6 +71,8 @@ def test_lowered_program_equals_stack_machine(harness, orc, funcs, L, layers, V)
     # ... with slots >= 1 marked deep (the harness checks that exactly those accesses use the deep opcodes)
     got3, need3, ninstr3, _ = run(harness, v, t, s, X, 1, use_sizes=7)
     assert same(got3, want) and (need3 == need).all() and (ninstr3 == ninstr2).all()
+    got4, need4, ninstr4, _ = run(harness, v, t, s, X, 1, use_sizes=5)   # default emission, deep pops / LOADs marked
+    assert same(got4, want) and (need4 == need).all() and (ninstr4 == ninstr).all()
 
 
 def test_multi_output_programs(harness, orc):
