@@ -252,12 +252,12 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "replay_kernel<16,false,false,true>", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak,
-                             "traffic": 53.2e6,   # dram read+write per launch, profiles/r1_final_ncu.txt
+                             "traffic": 53.6e6,   # dram read+write per launch, profiles/r1_final_ncu.txt
                              "traffic_source": "ncu --set full, profiles/r1_final_ncu.txt (same workload shard)",
                              "algorithmic_bytes": algorithmic_bytes(hi - lo, L, N, V, O), "peak_source": peak_src,
                              "kernel_ms": kms, "kernel_share_of_step": kms / float(np.mean(step_ms)),
-                             "issue_slots_busy_pct": 80.0,   # smsp__issue_active, same capture: the resource this kernel is bound by
-                             "note": "interpreter kernel: bound by instruction issue (80 % of issue slots busy, shared-memory pipe 61 %), not HBM (DESIGN.md 3.2)"},
+                             "issue_slots_busy_pct": 80.8,   # smsp__issue_active, same capture: the resource this kernel is bound by
+                             "note": "interpreter kernel: bound by instruction issue (81 % of issue slots busy, shared-memory pipe 62 %), not HBM (DESIGN.md 3.2)"},
                 "clocks": clocks, "wall_s_timed_region": t_wall, "fitness_mean_check": fit_host_check}
         if world == 1 and not args.no_cpu:
             v, ms, threads, sample = cpu_reference_leg(3, 1, target_seconds=10.0)

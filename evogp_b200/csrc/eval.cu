@@ -626,9 +626,11 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         const size_t data = per_dp * a.NP;
         int warps = 8;
         if constexpr (K == 16) {
-            // one CTA per SM: as many warps as the registers (80 per thread at 768 threads) allow; their
-            // kTmemSlots16 slots of 16 columns fit the 512 columns with room to spare
-            warps = 32;
+            // one CTA per SM of up to 32 warps (64 registers each; 4 slots x 16 columns x 8 warps per lane quarter =
+            // the 512 columns), as many whole lane quarters as the shared memory left by the dataset holds
+            const size_t room = (size_t)g_max_smem > data ? (size_t)g_max_smem - data : 0;
+            warps = (int)(room / per_warp()) & ~3;
+            warps = warps > 32 ? 32 : (warps < 4 ? 4 : warps);
         }
         while (warps > 1 && data + warps * per_warp() > (size_t)g_max_smem) warps >>= 1;
         size_t smem = data + warps * per_warp();
@@ -670,7 +672,7 @@ struct ReplayChoice {
     int K;
     bool tmem;
 };
-static ReplayChoice choose_replay(bool multi, int mode, int N, int depth) {
+static ReplayChoice choose_replay(bool multi, int mode, int N, int depth, int Lp, size_t dataset_bytes) {
     ReplayChoice c{1, false};
     if (mode == MODE_ROWWISE) return c;
     c.K = choose_k(N);
@@ -681,7 +683,12 @@ static ReplayChoice choose_replay(bool multi, int mode, int N, int depth) {
     const int d = depth > 0 ? depth : 1;
     const double c8 = (double)((N + 255) / 256) * (14.0 + 16.0), c16 = (double)((N + 511) / 512) * (14.0 + 32.0);
     const bool want16 = g_force_k ? g_force_k == 16 : c16 < c8;
-    if (want16) { c.K = 16; c.tmem = true; }
+    // K = 16 needs room for >= 16 warps' program buffers and deep slots next to the dataset (very wide rows do not
+    // leave it: they run on the 8-datapoint kernels)
+    const size_t per_warp16 = (size_t)2 * Lp * 8 + (size_t)(d > kTmemSlots16 ? d - kTmemSlots16 : 0) * 512 * 4 + 16;
+    const size_t staged = dataset_bytes < 48 * 1024 ? dataset_bytes : 48 * 1024;   // larger datasets are tiled to <= 48 KB
+    const bool fits16 = staged + 16 * per_warp16 <= (size_t)g_max_smem;
+    if (want16 && (fits16 || g_force_k == 16)) { c.K = 16; c.tmem = true; }
     else if (tmem_stack_cols(8, d, 8) <= 128) c.tmem = true;
     return c;
 }
@@ -721,7 +728,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
-    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth);
+    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth, prog_pitch(L), (size_t)N * (V + (mode <= MODE_ABS ? O : 0)) * 4);
     const int deep_from = choice.K == 16 ? kTmemSlots16 : kNoDeepSlots;
     rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, kNoDeepSlots, st)
                : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16 && g_k16_split, deep_from, st);
