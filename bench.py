@@ -49,6 +49,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.active, self.ready = False, threading.Event()   # NVML is initialised before the timed region; samples only inside it
 
     def run(self):
         try:
@@ -60,7 +61,11 @@ class ClockSampler(threading.Thread):
                      "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                      "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                      "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            self.ready.set()
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.0005)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -72,6 +77,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.002)
         except Exception as e:   # NVML missing: report that rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -161,19 +167,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     mean_len = float(torch.stack([p.batch_subtree_size[:, 0].float().mean() for p in pops]).mean())
 
+    # N > 1: the fitness all-gather is fused into the evaluation kernel (stores into every rank's buffer through
+    # peer-mapped symmetric memory, then one inter-GPU barrier); NCCL all-gather when symmetric memory is unavailable
+    exch = None
+    if world > 1:
+        from evogp_b200.parallel import FitnessExchange
+        exch = FitnessExchange(P_total, dev)
+    exchange_kind = ("none (1 GPU)" if world == 1 else
+                     ("fused into the evaluation kernel over peer-mapped memory + barrier" if exch.available
+                      else "NCCL all_gather (symmetric memory unavailable: %s)" % exch.why))
+
     def step(i):
-        fit = pops[i % R].SR_fitness(X, y)
-        if world > 1:
-            fit = all_gather_fitness(fit, P_total)
-        return fit
+        if exch is not None:
+            return exch.sr_fitness(pops[i % R], X, y)
+        return pops[i % R].SR_fitness(X, y)
 
     abi = _native.abi()
+    sampler = ClockSampler(local); sampler.start()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
+    sampler.ready.wait(timeout=10)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
     launches0 = _native.launch_count()
     # Device-side timing, no host synchronisation inside the timed region: one event pair around the K steps gives the
     # total, one pair per step (recorded inside the C ABI around the replay launch) the kernel's own duration.
@@ -187,6 +203,7 @@ def run_ours(args):
         dist.barrier()
         torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
+    sampler.active = True
     ev_t0.record()
     for i in range(args.steps):
         abi.evogp_eval_set_timing_events(ctypes.c_void_p(kev[i][0].cuda_event), ctypes.c_void_p(kev[i][1].cuda_event))
@@ -194,6 +211,7 @@ def run_ours(args):
     ev_t1.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    sampler.active = False
     abi.evogp_eval_set_timing_events(None, None)
     kern_ms = [a.elapsed_time(b) for a, b in kev]
     launches = _native.launch_count() - launches0
@@ -246,7 +264,7 @@ def run_ours(args):
                 "config": dict(CFG, population_total=P_total, mean_tree_len=round(mean_len, 2),
                                l2="inputs rotate over %d populations (%.0f MB + %.0f MB programs) > 126 MB L2"
                                   % (R, R * (hi - lo) * L * 8 / 1e6, (hi - lo) * L * 8 / 1e6),
-                               parallelism="population replicated, eval sharded x%d, one all_gather of fitness" % world),
+                               parallelism="population replicated, eval sharded x%d, fitness exchange: %s" % (world, exchange_kind)),
                 "e2e": {"value": e2e_value, "unit": "tree-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "path": "evogp_SR_fitness_host (C ABI, pinned host buffers, chunked copy/compute overlap)"},
                 "gpu_launches": int(launches),
@@ -287,8 +305,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's CUDA kernels")

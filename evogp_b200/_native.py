@@ -19,7 +19,7 @@ _ops_loaded = False
 ABI_SYMBOLS = (
     "evogp_version", "evogp_last_error", "evogp_launch_count", "evogp_generate", "evogp_mutate", "evogp_crossover",
     "evogp_eval_workspace_bytes", "evogp_eval_set_timing_events", "evogp_evaluate", "evogp_SR_fitness", "evogp_batch_forward",
-    "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation",
+    "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation", "evogp_SR_fitness_scatter",
 )
 
 
@@ -50,6 +50,8 @@ def abi():
     L.evogp_evaluate.argtypes = [u, u, u, u, vp, vp, vp, vp, vp, vp, sz, vp]
     L.evogp_SR_fitness.argtypes = [u, u, u, u, u, i, vp, vp, vp, vp, vp, vp, u, vp, sz, vp]
     L.evogp_batch_forward.argtypes = [u, u, u, u, u, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.evogp_SR_fitness_scatter.argtypes = [u, u, u, u, u, i, vp, vp, vp, vp, vp, vp, vp, u, u, vp, sz, vp]
+    L.evogp_SR_fitness_scatter.restype = i
     L.evogp_SR_fitness_host.argtypes = [u, u, u, u, u, i, vp, vp, vp, vp, vp, vp, i]
     L.evogp_host_release.restype = None
     L.evogp_next_generation.restype = i

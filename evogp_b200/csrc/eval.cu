@@ -28,9 +28,16 @@ namespace evogp {
 
 enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_OUTPUT = 2, MODE_ROWWISE = 3 };
 
+// Fitness exchange fused into the evaluation kernel (multi-GPU): every tree's fitness is stored straight into each
+// rank's full-population buffer through peer-mapped memory (NVLink), at row_offset + tree.
+struct Scatter {
+    float *const *peers = nullptr;   // DEVICE array of `world` pointers, one full-population fitness buffer per rank
+    int world = 0;
+    unsigned row_offset = 0;
+};
 int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value, const int16_t *type,
              const int16_t *size, int len_stride, const float *X, const float *labels, float *out, void *workspace,
-             size_t workspace_bytes, void *stream);
+             size_t workspace_bytes, void *stream, Scatter scatter = Scatter());
 
 
 
@@ -49,6 +56,10 @@ struct ReplayArgs {
     // datapoint tiling (dataset larger than the shared-memory staging area): this launch covers datapoints
     // [d_base, d_base + N) of N_total; loss modes carry the running sum in out[] between launches
     int d_base, N_total, first_tile, last_tile;
+    // multi-GPU: on the last tile also store the fitness into every rank's buffer (Scatter)
+    float *const *peers;
+    int world;
+    unsigned row_offset;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -449,10 +460,11 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
         if (g.mode <= MODE_ABS) {
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) err += __shfl_xor_sync(0xffffffffu, err, s);
-            if (lane == 0) {
-                if (!g.first_tile) err += g.out[tree];                        // running sum of the earlier tiles
-                g.out[tree] = g.last_tile ? err / (float)(unsigned)g.N_total : err;   // forward.cu:478
-            }
+            if (!g.first_tile) err += g.out[tree];                            // running sum of the earlier tiles
+            const float fit = g.last_tile ? err / (float)(unsigned)g.N_total : err;   // forward.cu:478
+            if (lane == 0) g.out[tree] = fit;
+            // fused all-gather: lane r stores into rank r's buffer over NVLink (peer-mapped memory)
+            if (g.peers != nullptr && g.last_tile && lane < g.world) g.peers[lane][g.row_offset + (unsigned)tree] = fit;
         }
         __syncwarp();   // every lane is done with prog[buf] before lane 0 re-targets it
         buf ^= 1;
@@ -709,8 +721,10 @@ static int launch_replay(const ReplayArgs &a, int depth, ReplayChoice c, cudaStr
 
 int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value,
              const int16_t *type, const int16_t *size, int len_stride, const float *X, const float *labels, float *out,
-             void *workspace, size_t workspace_bytes, void *stream) {
+             void *workspace, size_t workspace_bytes, void *stream, Scatter scatter) {
     EVOGP_REQUIRE(P > 0, "popSize must be larger than 0, got %u", P);
+    EVOGP_REQUIRE(scatter.peers == nullptr || (scatter.world >= 1 && scatter.world <= 32 && mode <= MODE_ABS),
+                  "fitness scatter: world must be in [1, 32] (got %d) and the mode a loss mode", scatter.world);
     EVOGP_REQUIRE(L > 0 && L <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, L);
     EVOGP_REQUIRE(V > 0 && V <= 512, "var_len must be in (0, 512], got %u", V);   // forward.cu:320 asserts the same bound
     EVOGP_REQUIRE(O > 0 && O <= 256, "out_len must be in (0, 256], got %u", O);
@@ -737,6 +751,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     a.prog = w.prog; a.sched = w.sched; a.X = X; a.labels = labels; a.out = out;
     a.P = (int)P; a.Lp = prog_pitch(L); a.N = (int)N; a.V = (int)V; a.O = (int)O;
     a.NP = 0; a.npass = 0; a.depth = depth; a.mode = mode;
+    a.peers = scatter.peers; a.world = scatter.world; a.row_offset = scatter.row_offset;
     return multi ? launch_replay<true>(a, depth, choice, st) : launch_replay<false>(a, depth, choice, st);
 }
 
@@ -776,6 +791,18 @@ extern "C" int evogp_SR_fitness(unsigned popSize, unsigned dataPoints, unsigned 
     (void)kernel_type;   // reference execute_mode 0..4 (forest.py:340-347): one kernel serves all
     return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
                     subtree_size, (int)gpLen, variables, labels, fitnesses, workspace, workspace_bytes, stream);
+}
+
+extern "C" int evogp_SR_fitness_scatter(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,
+                                        unsigned outLen, int useMSE, const float *value, const int16_t *type,
+                                        const int16_t *subtree_size, const float *variables, const float *labels,
+                                        float *fitnesses, float *const *peer_fitnesses, unsigned world, unsigned row_offset,
+                                        void *workspace, size_t workspace_bytes, void *stream) {
+    EVOGP_REQUIRE(peer_fitnesses != nullptr, "peer_fitnesses must not be NULL");
+    Scatter sc;
+    sc.peers = peer_fitnesses; sc.world = (int)world; sc.row_offset = row_offset;
+    return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
+                    subtree_size, (int)gpLen, variables, labels, fitnesses, workspace, workspace_bytes, stream, sc);
 }
 
 extern "C" int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,

@@ -6,7 +6,15 @@ genetic operators would need an all-gather of P*L*8 bytes per generation; recomp
 every rank from the same seeds costs less and keeps the collective to 4 bytes per individual.
 Populations stay bit-identical across ranks because every genetic kernel is a deterministic
 integer move and every rank consumes identical RNG streams (see `seed_all`).
+
+The exchange itself comes in two forms: `all_gather_fitness` (one NCCL all-gather; gloo in the CPU
+tests) and `FitnessExchange` (NVLink boxes): the evaluation kernel stores every fitness straight
+into each rank's full-population buffer through peer-mapped symmetric memory
+(`evogp_SR_fitness_scatter`), so the all-gather is fused into the kernel and only a ~7 us
+inter-GPU barrier follows it.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -44,22 +52,97 @@ def seed_all(seed: int):
         torch.cuda.manual_seed_all(seed)
 
 
-class ShardedSymbolicRegression:
-    """Wraps a SymbolicRegression problem: evaluate() runs SR_fitness on this rank's row shard
-    and all-gathers.  Drop-in for `problem` in StandardPipeline / GeneticProgramming loops."""
+class FitnessExchange:
+    """Fitness all-gather fused into the evaluation kernel over peer-mapped memory.
 
-    def __init__(self, problem, group=None):
+    Two full-population fitness buffers in torch symmetric memory (peer-mapped over NVLink / NVSwitch), used
+    alternately: the kernel of generation g stores into buffer g % 2 of every rank while a slower rank may still be
+    reading generation g - 1 from the other one; the barrier after each kernel keeps ranks at most one generation
+    apart, so two buffers are enough.  `available` is False (reason in `why`) when symmetric memory cannot be set up
+    (gloo / CPU, no peer access); callers then use `all_gather_fitness`."""
+
+    def __init__(self, pop_size: int, device, group=None):
+        self.pop_size, self.group = pop_size, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.lo, self.hi, _ = shard_bounds(pop_size, self.world, self.rank)
+        self.available, self.why, self._turn = False, "", 0
+        self._bufs, self._handles = [], []
+        if self.world > 32:
+            self.why = "more than 32 ranks"
+            return
+        try:
+            if dist.get_backend(group) != "nccl":
+                raise RuntimeError("backend is not nccl")
+            import torch.distributed._symmetric_memory as symm
+
+            for _ in range(2):
+                buf = symm.empty(pop_size, dtype=torch.float32, device=device)
+                self._handles.append(symm.rendezvous(buf, group if group is not None else dist.group.WORLD))
+                self._bufs.append(buf)
+                buf.zero_()
+            self._handles[0].barrier(channel=0)
+            self.available = True
+        except Exception as e:   # no symmetric memory here: fall back to the NCCL all-gather
+            self.why = f"{type(e).__name__}: {e}"
+            self._bufs, self._handles = [], []
+
+    def sr_fitness(self, shard, datapoints, labels, use_MSE: bool = True):
+        """shard: this rank's rows [lo, hi) as a Forest.  Returns the full-population fitness [pop_size]."""
+        from . import _native
+
+        assert shard.pop_size == self.hi - self.lo, "shard does not match this rank's row range"
+        if not self.available:
+            return all_gather_fitness(shard.SR_fitness(datapoints, labels, use_MSE), self.pop_size, self.group)
+        turn = self._turn & 1
+        self._turn += 1
+        buf, hdl = self._bufs[turn], self._handles[turn]
+        if shard.pop_size > 0:
+            abi = _native.abi()
+            dev = shard.batch_node_value.device
+            P, L = shard.batch_node_value.shape
+            N, V = datapoints.shape
+            O = labels.shape[1] if labels.dim() > 1 else 1
+            ws_bytes = abi.evogp_eval_workspace_bytes(P, L)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            local = torch.empty(P, dtype=torch.float32, device=dev)
+            vp = lambda t: ctypes.c_void_p(t.data_ptr())
+            rc = abi.evogp_SR_fitness_scatter(P, N, L, V, O, 1 if use_MSE else 0, vp(shard.batch_node_value),
+                                              vp(shard.batch_node_type), vp(shard.batch_subtree_size),
+                                              vp(datapoints.contiguous()), vp(labels.contiguous()), vp(local),
+                                              ctypes.c_void_p(hdl.buffer_ptrs_dev), self.world, self.lo, vp(ws),
+                                              ctypes.c_size_t(ws_bytes), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _native.check(rc, "evogp_SR_fitness_scatter")
+        hdl.barrier(channel=0)     # every rank's stores have landed; also orders this generation against the next
+        return buf
+
+
+class ShardedSymbolicRegression:
+    """Wraps a SymbolicRegression problem: evaluate() runs SR_fitness on this rank's row shard and exchanges the
+    fitness - fused into the kernel over peer memory when symmetric memory is available (`FitnessExchange`), else
+    one NCCL / gloo all-gather.  Drop-in for `problem` in StandardPipeline / GeneticProgramming loops."""
+
+    def __init__(self, problem, group=None, fused_exchange: bool = True):
         self.problem = problem
         self.group = group
+        self.fused_exchange = fused_exchange
+        self._exchange = None
 
     def evaluate(self, forest, use_MSE: bool = True):
         world = dist.get_world_size(self.group)
         rank = dist.get_rank(self.group)
         lo, hi, _ = shard_bounds(forest.pop_size, world, rank)
+        dev = forest.batch_node_value.device
+        fused = (self.fused_exchange and dev.type == "cuda" and getattr(self.problem, "execute_mode", "") != "torch"
+                 and hasattr(self.problem, "datapoints"))
+        if fused:
+            if self._exchange is None or self._exchange.pop_size != forest.pop_size:
+                self._exchange = FitnessExchange(forest.pop_size, dev, self.group)
+            if self._exchange.available:
+                return -self._exchange.sr_fitness(forest[lo:hi], self.problem.datapoints, self.problem.labels, use_MSE)
         if hi > lo:
             local = self.problem.evaluate(forest[lo:hi], use_MSE)
         else:
-            local = torch.empty(0, dtype=torch.float32, device=forest.batch_node_value.device)
+            local = torch.empty(0, dtype=torch.float32, device=dev)
         return all_gather_fitness(local, forest.pop_size, self.group)
 
     @property

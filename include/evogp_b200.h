@@ -96,6 +96,18 @@ int evogp_SR_fitness(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsi
                      const float *variables, const float *labels, float *fitnesses, unsigned kernel_type,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Multi-GPU form of evogp_SR_fitness (SURVEY.md row e; no counterpart in the reference, which is single-GPU): this
+ * rank evaluates its shard of popSize trees and the kernel stores each fitness straight into EVERY rank's
+ * full-population buffer at [row_offset + i] through peer-mapped memory (NVLink) - the all-gather of the fitness
+ * scalars is fused into the evaluation kernel.  peer_fitnesses: DEVICE array of `world` (<= 32) device pointers, entry r
+ * = rank r's buffer (this rank's own included), mapped into this process (CUDA IPC / symmetric memory).  fitnesses:
+ * local [popSize] (also written).  The caller synchronises the ranks afterwards (any inter-GPU barrier on the stream). */
+int evogp_SR_fitness_scatter(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                             int useMSE, const float *value, const int16_t *type, const int16_t *subtree_size,
+                             const float *variables, const float *labels, float *fitnesses,
+                             float *const *peer_fitnesses, unsigned world, unsigned row_offset, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* Fused form of Forest.batch_forward (tree/forest.py:143-176), which the reference
  * implements by replicating the forest dataPoints times: results[P, N, O]. */
 int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,

@@ -34,6 +34,14 @@ def main():
     full = base.evaluate(forest)
     got = sharded.evaluate(forest)
     assert torch.equal(torch.nan_to_num(full, nan=-1.0), torch.nan_to_num(got, nan=-1.0)), "sharded != full"
+    fused = sharded._exchange is not None and sharded._exchange.available
+    why = "" if fused else (sharded._exchange.why if sharded._exchange is not None else "not attempted")
+    # the NCCL all-gather form must give the same answer
+    got2 = ShardedSymbolicRegression(base, fused_exchange=False).evaluate(forest)
+    assert torch.equal(torch.nan_to_num(full, nan=-1.0), torch.nan_to_num(got2, nan=-1.0)), "sharded (all-gather) != full"
+    for _ in range(5):     # alternating buffers, back to back
+        again = sharded.evaluate(forest)
+        assert torch.equal(torch.nan_to_num(full, nan=-1.0), torch.nan_to_num(again, nan=-1.0)), "repeat != full"
     algo = GeneticProgramming(forest, DefaultCrossover(), DefaultMutation(0.2, desc.update(max_layer_cnt=3)),
                               DefaultSelection(survival_rate=0.3, elite_rate=0.01))
     for gen in range(3):
@@ -52,7 +60,8 @@ def main():
         assert all(torch.equal(g, gathered[0]) for g in gathered), f"generation {gen}: populations diverged"
     dist.barrier()
     if rank == 0:
-        print(f"multi-gpu check ok on {world} ranks: sharded fitness bit-identical, populations identical for 3 generations")
+        print(f"multi-gpu check ok on {world} ranks: sharded fitness bit-identical, populations identical for 3 generations; "
+              f"fitness exchange fused into the kernel: {fused} {why}")
     dist.destroy_process_group()
 
 

@@ -321,6 +321,34 @@ def test_deep_operand_stacks(native, orc, shape, N):
     assert np.allclose(out, ref_out, rtol=1e-5, atol=1e-6, equal_nan=True)
 
 
+def test_fitness_scatter_into_peer_buffers(native, orc):
+    """evogp_SR_fitness_scatter: the fused all-gather.  On one GPU the 'peers' are three buffers of this device."""
+    import ctypes
+    v, t, s = make_forest(orc, 3001, 64, 3, 1, ARITH_FUNCS, 6, keys=(5, 9))
+    X, y = make_data(1024, 3, seed=3)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    want = G.abi_sr_fitness(native, dv, dt, ds, dX, dy)
+    abi = native.abi()
+    P, L = v.shape
+    total, off, world = 5000, 1234, 3
+    bufs = [torch.full((total,), -7.0, device="cuda") for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    local = torch.empty(P, device="cuda")
+    nbytes = abi.evogp_eval_workspace_bytes(P, L)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    vp = lambda a: ctypes.c_void_p(a.data_ptr())
+    for N in (1024, 100):     # 16 and 4 datapoints per lane
+        rc = abi.evogp_SR_fitness_scatter(P, N, L, 3, 1, 1, vp(dv), vp(dt), vp(ds), vp(dX), vp(dy), vp(local), vp(table), world, off,
+                                          vp(ws), ctypes.c_size_t(nbytes), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, abi.evogp_last_error()
+        torch.cuda.synchronize()
+        ref = want if N == 1024 else G.abi_sr_fitness(native, dv, dt, ds, dX[:N].contiguous(), dy[:N].contiguous())
+        same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+        assert same(local, ref)
+        for b in bufs:
+            assert same(b[off:off + P], ref) and bool((b[:off] == -7.0).all()) and bool((b[off + P:] == -7.0).all())
+
+
 def test_if_heavy_trees(native, orc):
     funcs = ["if", "if", "+", "<", "neg"]   # roulette normalises duplicates away; IF share is 1/4
     v, t, s = make_forest(orc, 4000, 121, 3, 1, ["if", "+", "<", "neg"], 5, keys=(13, 13), leaf_prob=0.1)
