@@ -18,7 +18,12 @@
 //        [var][datapoint].  Squared/absolute error is accumulated in registers and
 //        reduced with warp shuffles: one plain store per tree — no memset, no
 //        atomics on fitness, no averaging kernel.
-#include <cooperative_groups.h>
+//        Single-output programs keep their operand stack in TENSOR MEMORY (TSTK):
+//        tcgen05.st / tcgen05.ld of one K-column slot per save / restore, no MMA
+//        involved; K = 16 datapoints per lane in one 32-warp CTA per SM, K = 8 in
+//        four 8-warp CTAs.  Multi-GPU: the fitness all-gather is
+//        fused into the final store (Scatter: peer-mapped buffers over NVLink).
+#include <cstdlib>
 #include "lower.cuh"
 #include "fastpath_k8.inc"
 #include "fastpath_k8_tmem.inc"

@@ -114,6 +114,10 @@ full = all_gather_fitness(local, P)
 want = torch.from_numpy(oracle.sr_fitness(v, t, s, X, y))
 assert full.shape == (P,)
 assert torch.equal(torch.nan_to_num(full, nan=-1.0), torch.nan_to_num(want, nan=-1.0)), "gathered fitness differs"
+# the fused exchange needs NCCL + peer memory: on gloo it must decline (and say why), never half-initialise
+from evogp_b200.parallel import FitnessExchange
+ex = FitnessExchange(P, torch.device("cpu"))
+assert not ex.available and "nccl" in ex.why and (ex.lo, ex.hi) == (lo, hi)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
