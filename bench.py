@@ -285,16 +285,20 @@ def run_ours(args):
                     import oracle
                     if oracle.ref_gpu_available():
                         ref = oracle.ref_gpu()
-                        p0 = pops[0]
-                        ref.sr_fitness(p0.batch_node_value, p0.batch_node_type, p0.batch_subtree_size, X, y); torch.cuda.synchronize()
-                        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        for r in range(3):
+                        for r in range(3):   # warm-up: the reference kernel's local-memory frames are sized on first use
+                            p0 = pops[r % R]
+                            ref.sr_fitness(p0.batch_node_value, p0.batch_node_type, p0.batch_subtree_size, X, y)
+                        torch.cuda.synchronize()
+                        best = float("inf")
+                        for r in range(5):   # best of five single calls: the most favourable reading for the reference
                             pr = pops[(r + 1) % R]
+                            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                            e0.record()
                             ref.sr_fitness(pr.batch_node_value, pr.batch_node_type, pr.batch_subtree_size, X, y)
-                        e1.record(); torch.cuda.synchronize()
-                        line["reference_cuda_same_gpu"] = {"value": 3 * (hi - lo) * N / (e0.elapsed_time(e1) * 1e-3), "unit": "tree-evals/s",
-                                                           "what": "reference forward.cu SR_fitness(kernel_type=4) compiled unmodified for sm_100a (oracle/_ref)"}
+                            e1.record(); torch.cuda.synchronize()
+                            best = min(best, e0.elapsed_time(e1))
+                        line["reference_cuda_same_gpu"] = {"value": (hi - lo) * N / (best * 1e-3), "unit": "tree-evals/s",
+                                                           "what": "reference forward.cu SR_fitness(kernel_type=4) compiled unmodified for sm_100a (oracle/_ref); best of 5 calls"}
                 except Exception as e:
                     line["reference_cuda_same_gpu"] = {"unavailable": repr(e)}
         print(json.dumps(line))
