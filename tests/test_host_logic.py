@@ -52,6 +52,19 @@ def test_operator_library_registers_reference_schemas(native):
         assert [a.name for a in schema.arguments] == args
 
 
+def test_reference_front_end_import_path():
+    """The reference reaches its native code through `import evogp.evogp_cuda` (src/evogp/tree/__init__.py:2) and the
+    `evogp.tree / algorithm / problem / pipeline` modules; the shim provides every one of them."""
+    import importlib
+
+    mod = importlib.import_module("evogp.evogp_cuda")
+    assert mod is not None and hasattr(torch.ops.evogp_cuda, "tree_SR_fitness")
+    from evogp.tree import Forest, GenerateDescriptor          # noqa: F401
+    from evogp.algorithm import GeneticProgramming, DefaultSelection, DefaultMutation, DefaultCrossover   # noqa: F401
+    from evogp.problem import SymbolicRegression               # noqa: F401
+    from evogp.pipeline import StandardPipeline                # noqa: F401
+
+
 def test_scalar_argument_errors_need_no_gpu(native):
     L = native.abi()
     assert L.evogp_crossover(0, 1, 64, *([None] * 11)) == 1 and b"pop_size_ori" in L.evogp_last_error()
