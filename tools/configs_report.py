@@ -29,6 +29,19 @@ def ev_time(fn, reps=7, warm=2):
     return float(np.median(ts))
 
 
+def ref_time(fn):
+    """Reference kernels: best of five warmed-up calls (their first launches size local-memory frames and are erratic)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
 def sr_data(N, V):
     X = torch.rand(N, V, device="cuda") * 2 - 1
     y = (X[:, :1] ** 4 / (X[:, :1] ** 4 + 1) + X[:, 1:2] ** 4 / (X[:, 1:2] ** 4 + 1) + X[:, 2:].sum(1, keepdim=True) * 0.1).contiguous()
@@ -59,8 +72,29 @@ def main():
     ms = ev_time(lambda: f.SR_fitness(X, y))
     rep["config2_pop1e5_L64_N1024_V3"] = {"ms": ms, "tree_evals_per_s": 1e5 * 1024 / ms * 1e3}
     if ref:
-        rms = ev_time(lambda: ref.sr_fitness(f.batch_node_value, f.batch_node_type, f.batch_subtree_size, X, y), reps=3, warm=1)
+        rms = ref_time(lambda: ref.sr_fitness(f.batch_node_value, f.batch_node_type, f.batch_subtree_size, X, y))
         rep["config2_pop1e5_L64_N1024_V3"]["reference_cuda_ms"] = rms
+    # ---- SURVEY.md 8(d) variants of config 2: transcendental function set; post-evolution population ----
+    dt = GenerateDescriptor(max_tree_len=64, input_len=3, output_len=1, using_funcs=["+", "-", "*", "/", "sin", "cos", "tan"],
+                            max_layer_cnt=6, const_samples=[-1, 0, 1])
+    ft = Forest.random_generate(100000, dt)
+    ms_t = ev_time(lambda: ft.SR_fitness(X, y))
+    var = {"transcendental_funcs_ms": ms_t, "transcendental_tree_evals_per_s": 1e5 * 1024 / ms_t * 1e3,
+           "transcendental_mean_tree_len": float(ft.batch_subtree_size[:, 0].float().mean())}
+    if ref:
+        var["transcendental_reference_cuda_ms"] = ref_time(lambda: ref.sr_fitness(ft.batch_node_value, ft.batch_node_type, ft.batch_subtree_size, X, y))
+    prob2 = SymbolicRegression(datapoints=X, labels=y)
+    algo2 = GeneticProgramming(f, DefaultCrossover(), DefaultMutation(0.2, d.update(max_layer_cnt=3)), DefaultSelection(0.3, elite_rate=0.01))
+    for _ in range(20):
+        algo2.step(torch.nan_to_num(prob2.evaluate(algo2.forest), nan=float("-inf")))
+    fe = algo2.forest
+    ms_e = ev_time(lambda: fe.SR_fitness(X, y))
+    var.update({"after_20_generations_ms": ms_e, "after_20_generations_tree_evals_per_s": 1e5 * 1024 / ms_e * 1e3,
+                "after_20_generations_mean_tree_len": float(fe.batch_subtree_size[:, 0].float().mean())})
+    if ref:
+        var["after_20_generations_reference_cuda_ms"] = ref_time(lambda: ref.sr_fitness(fe.batch_node_value, fe.batch_node_type, fe.batch_subtree_size, X, y))
+    rep["config2_variants"] = var
+    del ft, fe, algo2
     # ---- config 3: pop 1e6, V 10 ----
     X, y = sr_data(1024, 10)
     d = GenerateDescriptor(max_tree_len=64, input_len=10, output_len=1, using_funcs=funcs, max_layer_cnt=6, const_samples=[-1, 0, 1])
@@ -72,7 +106,7 @@ def main():
     rep["config3_pop1e6_L64_N1024_V10"] = {"one_gpu_full_population_ms": ms_full, "tree_evals_per_s_one_gpu": 1e6 * 1024 / ms_full * 1e3,
                                            "per_gpu_shard_of_8_ms": ms_shard}
     if ref:
-        rms = ev_time(lambda: ref.sr_fitness(shard.batch_node_value, shard.batch_node_type, shard.batch_subtree_size, X, y), reps=3, warm=1)
+        rms = ref_time(lambda: ref.sr_fitness(shard.batch_node_value, shard.batch_node_type, shard.batch_subtree_size, X, y))
         rep["config3_pop1e6_L64_N1024_V10"]["reference_cuda_shard_ms"] = rms
     del f, shard
     # ---- config 4: multi-output classification shape ----
