@@ -84,7 +84,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_leg(steps, warmup, target_seconds=12.0):
+def cpu_reference_leg(steps, warmup, target_seconds=20.0):
     """The reference has no CPU implementation of this path (torch_wrapper.cu:301-307 registers CUDA only):
     the CPU arm is the oracle's restatement, all host threads, on a bounded sample of the same workload."""
     import oracle
@@ -105,8 +105,9 @@ def cpu_reference_leg(steps, warmup, target_seconds=12.0):
 
     probe = forest(2048, 0)
     t0 = time.perf_counter(); oracle.sr_fitness(*probe, X, y, nthreads=threads); dt = time.perf_counter() - t0
-    per_step = max(target_seconds / max(steps + warmup, 1), 0.5)
-    sample = int(min(CFG["pop_per_gpu"], max(2048, 2048 * per_step / dt)))
+    # bounded sample: the whole --steps K --warmup W run takes about target_seconds whatever K is (>= 512 trees per step)
+    per_step = target_seconds / max(steps + warmup, 1)
+    sample = int(min(CFG["pop_per_gpu"], max(512, 2048 * per_step / dt)))
     pops = [forest(sample, k) for k in range(2)]
     for i in range(warmup):
         oracle.sr_fitness(*pops[i % 2], X, y, nthreads=threads)
