@@ -50,6 +50,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.active, self.ready = False, threading.Event()   # NVML is initialised before the timed region; samples only inside it
+        self.force = False    # one extra sample right after a timed region too short to catch one
 
     def run(self):
         try:
@@ -63,9 +64,10 @@ class ClockSampler(threading.Thread):
                      "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
             self.ready.set()
             while not self.stop_flag:
-                if not self.active:
+                if not (self.active or self.force):
                     time.sleep(0.0005)
                     continue
+                self.force = False
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -213,6 +215,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     sampler.active = False
+    if not sampler.samples:     # very short runs: read the clocks immediately after the last step
+        sampler.force = True
+        time.sleep(0.02)
     abi.evogp_eval_set_timing_events(None, None)
     kern_ms = [a.elapsed_time(b) for a, b in kev]
     launches = _native.launch_count() - launches0
