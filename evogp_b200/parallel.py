@@ -14,6 +14,7 @@ into each rank's full-population buffer through peer-mapped symmetric memory
 inter-GPU barrier follows it.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -69,6 +70,9 @@ class FitnessExchange:
         self._bufs, self._handles = [], []
         if self.world > 32:
             self.why = "more than 32 ranks"
+            return
+        if os.environ.get("EVOGP_FUSED_EXCHANGE", "1") == "0":
+            self.why = "disabled by EVOGP_FUSED_EXCHANGE=0"
             return
         try:
             if dist.get_backend(group) != "nccl":
