@@ -121,6 +121,26 @@ def cpu_reference_leg(steps, warmup, target_seconds=20.0):
     return value, total / steps * 1e3, threads, f"{sample} of {CFG['pop_per_gpu']} trees x {N} datapoints per step (same generator, same dataset)"
 
 
+class StdoutGuard:
+    """Keeps stdout to the ONE JSON line: while active, file descriptor 1 points at stderr, so banners that native
+    libraries write to stdout (NCCL prints its version there) cannot precede the result; emit() writes to the real one."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,7 +154,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
 
@@ -307,7 +327,7 @@ def run_ours(args):
                                                            "what": "reference forward.cu SR_fitness(kernel_type=4) compiled unmodified for sm_100a (oracle/_ref); best of 5 calls"}
                 except Exception as e:
                     line["reference_cuda_same_gpu"] = {"unavailable": repr(e)}
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -324,7 +344,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with StdoutGuard() as out:
+            run_ours(args, out)
 
 
 if __name__ == "__main__":
