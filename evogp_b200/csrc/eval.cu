@@ -465,7 +465,10 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
         if (g.mode <= MODE_ABS) {
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) err += __shfl_xor_sync(0xffffffffu, err, s);
-            if (!g.first_tile) err += g.out[tree];                            // running sum of the earlier tiles
+            if (!g.first_tile) {                                              // running sum of the earlier tiles:
+                float prev = lane == 0 ? g.out[tree] : 0.0f;                  // lane 0 reads (it is the one that writes)
+                err += __shfl_sync(0xffffffffu, prev, 0);
+            }
             const float fit = g.last_tile ? err / (float)(unsigned)g.N_total : err;   // forward.cu:478
             if (lane == 0) g.out[tree] = fit;
             // fused all-gather: lane r stores into rank r's buffer over NVLink (peer-mapped memory)
