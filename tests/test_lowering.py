@@ -139,6 +139,10 @@ def test_stack_need_of_worst_case_shapes(harness, orc, kind, depth, expect_need)
     assert same(got, orc.batch_forward(v, t, s, X, 1))
     assert need[0] == expect_need and maxsp[0] == expect_need
     assert need[0] <= harness.harness_depth_bound(len(nodes))
+    # the same worst cases through the other emission modes: split, deep slots (>= 1) marked, both
+    for flags in (3, 5, 7):
+        got_f, need_f, _, maxsp_f = run(harness, v, t, s, X, 1, use_sizes=flags)
+        assert same(got_f, got) and need_f[0] == expect_need and maxsp_f[0] == expect_need
 
 
 def test_malformed_rows_lower_to_nan(harness, orc):
