@@ -17,7 +17,15 @@ LIB_SO = os.path.join(LIBDIR, "libevogp_b200.so")
 OPS_SO = os.path.join(LIBDIR, "evogp_cuda_ops.so")
 
 CU_SOURCES = ["runtime.cu", "eval.cu", "splice.cu", "generate.cu", "nextgen.cu", "host_api.cu"]
-CU_HEADERS = ["common.cuh", "program.cuh", "lower.cuh", "fastpath_k8.inc", "gen_tree.cuh", "../../include/evogp_b200.h"]
+
+
+def _headers():
+    """Everything a .cu may include: every .cuh / generated .inc in csrc/ (and the generator itself), plus the C ABI header."""
+    import glob
+
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc"))
+                  + glob.glob(os.path.join(CSRC, "gen_*.py"))) + [os.path.normpath(os.path.join(CSRC, "../../include/evogp_b200.h"))]
+
 
 # -use_fast_math: the reference's numeric contract (its setup.py passes the same flag), see DESIGN.md
 NVCC_FLAGS = ["-O3", "-std=c++17", "-use_fast_math", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,7 +42,7 @@ def _stale(target, deps):
 def build_lib(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
-    hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in CU_HEADERS]
+    hdrs = _headers()
     objs = []
     procs = []
     for s in srcs:

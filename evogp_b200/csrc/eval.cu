@@ -491,7 +491,11 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
+// device properties of the CURRENT device (refreshed whenever the calling thread's device changes: one process may
+// drive several GPUs; cudaFuncSetAttribute and occupancy answers are per device too, so nothing below caches them
+// across devices)
+static thread_local int g_props_dev = -1;
+static thread_local int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
 // EVOGP_TMEM_STACK=0 keeps the operand stack in shared memory (the A/B switch of profiles/; default on)
 static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_STACK"); return !(e && e[0] == '0'); }();
 // EVOGP_K16_SPLIT=1 feeds the K = 16 kernel split-mode programs (lower.cuh; the A/B switch of profiles/; default off)
@@ -501,12 +505,13 @@ static const int g_force_k = []() { const char *e = getenv("EVOGP_REPLAY_K"); re
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
 
 static int device_props() {
-    if (g_sm_count) return EVOGP_OK;
     int dev = 0;
     EVOGP_CUDA(cudaGetDevice(&dev));
+    if (dev == g_props_dev) return EVOGP_OK;
     EVOGP_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     EVOGP_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     EVOGP_CUDA(cudaDeviceGetAttribute(&g_smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    g_props_dev = dev;
     return EVOGP_OK;
 }
 
@@ -528,8 +533,6 @@ static Workspace carve(void *ws, unsigned P, unsigned L) {
     return w;
 }
 
-constexpr int kTmemSlots16 = 4;   // K = 16: operand-stack slots kept in tensor memory (deeper ones: shared memory)
-
 template <bool MULTI, bool SPLIT>
 static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
                           const int16_t *type, const int16_t *size, int len_stride, int depth, int deep_from, cudaStream_t st) {
@@ -539,11 +542,7 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     int warps = 8;
     while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
     const size_t smem = warps * per_warp;
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && attr_set < smem) {
-        EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: not cached
     LowerArgs a;
     a.value = value; a.type = type; a.size = size;
     a.prog = w.prog; a.sched = w.sched;
@@ -552,13 +551,14 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.deep_from = deep_from;
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
-    static int per_sm_cached = 0;
-    static size_t per_sm_smem = ~(size_t)0;
-    if (per_sm_smem != smem) {
+    static thread_local int per_sm_cached = 0, per_sm_dev = -1;
+    static thread_local size_t per_sm_smem = ~(size_t)0;
+    if (per_sm_smem != smem || per_sm_dev != g_props_dev) {
         int n = 0;
         EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem));
         per_sm_cached = n < 1 ? 1 : n;
         per_sm_smem = smem;
+        per_sm_dev = g_props_dev;
     }
     long long grid = ((long long)P + warps - 1) / warps;
     const long long cap = (long long)g_sm_count * per_sm_cached;
@@ -578,13 +578,29 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
     return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
 }
 
+constexpr int kTmemSlots16 = 4;   // K = 16: operand-stack slots kept in tensor memory (deeper ones: shared memory)
+
+// shared memory one warp of a replay CTA needs: two program rows, its shared-memory stack slots, multi-output accumulators
+static size_t replay_per_warp(int K, bool multi, bool tmem, int depth, int Lp, int O) {
+    const size_t SLOT = 32 * (size_t)K;
+    int smem_depth = multi ? 1 : (depth > 0 ? depth : 1);
+    if (tmem) smem_depth = K == 16 ? (depth > kTmemSlots16 ? depth - kTmemSlots16 : 0) : 0;
+    return (size_t)2 * Lp * 8 + (size_t)smem_depth * SLOT * 4 + (multi ? (size_t)O * SLOT * 4 : 0) + 16;
+}
+// does ONE pass (32 * K datapoints of `per_dp` bytes each) fit next to four warps?  Wide datasets (hundreds of
+// inputs) push the choice down to K = 4 / 1 instead of failing (the reference accepts var_len <= 512)
+static bool replay_fits(int K, bool multi, bool tmem, int depth, int Lp, int O, size_t per_dp) {
+    return (size_t)32 * K * per_dp + 4 * replay_per_warp(K, multi, tmem, depth, Lp, O) <= (size_t)g_max_smem;
+}
+
 // cost model for choosing K: issue slots per datapoint ~ (dispatch overhead + K) / K, times padding waste
-static int choose_k(int N) {
+static int choose_k(int N, bool multi, int depth, int Lp, int O, size_t per_dp) {
     const int ks[3] = {8, 4, 1};
     int best = 1;
     double best_cost = 1e30;
     for (int i = 0; i < 3; ++i) {
         const int K = ks[i];
+        if (K > 1 && !replay_fits(K, multi, false, depth, Lp, O, per_dp)) continue;
         const int npass = (N + 32 * K - 1) / (32 * K);
         const double cost = (double)npass * (14.0 + 2.0 * K);
         if (cost < best_cost) { best_cost = cost; best = K; }
@@ -625,10 +641,10 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         size_t room = 48 * 1024;
         if (room + 4 * per_warp() > (size_t)g_max_smem) room = (size_t)g_max_smem > 4 * per_warp() ? (size_t)g_max_smem - 4 * per_warp() : 0;
         tile = (int)(room / per_dp / SLOT) * SLOT;
-        if (tile < SLOT) tile = ((size_t)SLOT * per_dp + 4 * per_warp() <= (size_t)g_max_smem) ? SLOT : 0;
+        if (tile < SLOT) tile = ((size_t)SLOT * per_dp + per_warp() <= (size_t)g_max_smem) ? SLOT : 0;   // one pass, as many warps as fit
         if (tile >= a.NP) tile = a.NP;
-        if (tile < SLOT || (a.N + tile - 1) / tile > 64) {
-            set_error("%d inputs + %d labels per datapoint do not fit the %d B shared-memory staging area", a.V, a.O, g_max_smem);
+        if (tile < SLOT) {   // cannot happen: choose_replay picks a K whose single pass fits (replay_fits)
+            set_error("one pass of %d datapoints x (%d inputs + %d labels) does not fit the %d B shared-memory staging area", SLOT, a.V, a.O, g_max_smem);
             return EVOGP_ERR_UNSUPPORTED;
         }
     }
@@ -642,7 +658,10 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         a.d_base = d0; a.N_total = N_total; a.first_tile = d0 == 0; a.last_tile = d0 + tile >= N_total;
         if (!ROWWISE) a.X = X0 + (size_t)d0 * a.V;
         if (Y0) a.labels = Y0 + (size_t)d0 * a.O;
-        a.sched = sched0 + t;                                  // one ticket counter per launch (64 zeroed by lower_kernel)
+        // one ticket counter per launch: the 64 words lower_kernel zeroed, reused round-robin (launches are ordered
+        // on the stream, so word t % 64 is idle again by the time launch t is enqueued)
+        a.sched = sched0 + (t & 63);
+        if (t >= 64) EVOGP_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(unsigned), st));
         const size_t data = per_dp * a.NP;
         int warps = 8;
         if constexpr (K == 16) {
@@ -692,10 +711,11 @@ struct ReplayChoice {
     int K;
     bool tmem;
 };
-static ReplayChoice choose_replay(bool multi, int mode, int N, int depth, int Lp, size_t dataset_bytes) {
+static ReplayChoice choose_replay(bool multi, int mode, int N, int depth, int Lp, int O, size_t per_dp) {
     ReplayChoice c{1, false};
     if (mode == MODE_ROWWISE) return c;
-    c.K = choose_k(N);
+    const size_t dataset_bytes = (size_t)N * per_dp;
+    c.K = choose_k(N, multi, depth, Lp, O, per_dp);
     if (multi || c.K != 8 || !g_use_tmem_stack) return c;
     // tensor-memory stack while two warps per lane quarter fit the columns (depth <= 8, i.e. max_tree_len <= 256);
     // 16 datapoints per lane when that does not waste passes on padding (cost model of choose_k;
@@ -707,7 +727,7 @@ static ReplayChoice choose_replay(bool multi, int mode, int N, int depth, int Lp
     // leave it: they run on the 8-datapoint kernels)
     const size_t per_warp16 = (size_t)2 * Lp * 8 + (size_t)(d > kTmemSlots16 ? d - kTmemSlots16 : 0) * 512 * 4 + 16;
     const size_t staged = dataset_bytes < 48 * 1024 ? dataset_bytes : 48 * 1024;   // larger datasets are tiled to <= 48 KB
-    const bool fits16 = staged + 16 * per_warp16 <= (size_t)g_max_smem;
+    const bool fits16 = staged + 16 * per_warp16 <= (size_t)g_max_smem && (size_t)512 * per_dp + 16 * per_warp16 <= (size_t)g_max_smem;
     if (want16 && (fits16 || g_force_k == 16)) { c.K = 16; c.tmem = true; }
     else if (tmem_stack_cols(8, d, 8) <= 128) c.tmem = true;
     return c;
@@ -750,7 +770,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
-    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth, prog_pitch(L), (size_t)N * (V + (mode <= MODE_ABS ? O : 0)) * 4);
+    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth, prog_pitch(L), (int)O, ((size_t)V + (mode <= MODE_ABS ? O : 0)) * 4);
     const int deep_from = choice.K == 16 ? kTmemSlots16 : kNoDeepSlots;
     rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, kNoDeepSlots, st)
                : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16 && g_k16_split, deep_from, st);

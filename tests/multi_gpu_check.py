@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Manual multi-GPU check (not collected by pytest): run with
+"""Multi-GPU check, spawned by tests/test_multi_gpu.py (-m gpu, >= 2 GPUs) or by hand:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 Verifies, over NCCL: (1) sharded SR fitness + one all-gather == the full evaluation, bit for bit;
 (2) populations stay bit-identical on every rank across generations without exchanging trees."""
@@ -58,6 +58,20 @@ def main():
         gathered = [torch.empty_like(digest) for _ in range(world)]
         dist.all_gather(gathered, digest)
         assert all(torch.equal(g, gathered[0]) for g in gathered), f"generation {gen}: populations diverged"
+    # the fused generation step (one kernel, Philox draws keyed by the generation's keys): replicated populations stay
+    # identical on every rank, evaluation sharded with the fitness exchange fused into the kernel
+    from evogp_b200.algorithm import FusedGeneticProgramming
+    seed_all(1)
+    fused_algo = FusedGeneticProgramming(Forest.random_generate(60001, desc), desc.update(max_layer_cnt=3), 0.2, 0.3, elite_rate=0.01)
+    sharded2 = ShardedSymbolicRegression(base)
+    for gen in range(3):
+        fused_algo.step(sharded2.evaluate(fused_algo.forest))
+        f = fused_algo.forest
+        digest = torch.stack([f.batch_node_value.view(torch.int32).long().sum(), f.batch_node_type.long().sum(),
+                              f.batch_subtree_size.long().sum()])
+        gathered = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(gathered, digest)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), f"fused generation {gen}: populations diverged"
     dist.barrier()
     if rank == 0:
         print(f"multi-gpu check ok on {world} ranks: sharded fitness bit-identical, populations identical for 3 generations; "

@@ -222,6 +222,43 @@ def test_datasets_larger_than_shared_memory_are_tiled(native, orc, ref, pop, L, 
         G.assert_close_fitness(bf[sub], want_bf, rtol=5e-3, atol=1e-5, what="tiled batch_forward")
 
 
+@pytest.mark.parametrize("pop,L,V,O,N,funcs,layers", [(200, 64, 300, 1, 200, ARITH_FUNCS, 6),       # one 512-datapoint pass of 301 floats does not fit
+                                                       (150, 64, 512, 1, 129, ARITH_FUNCS, 6),       # the reference's var_len bound
+                                                       (100, 32, 256, 8, 77, EXACT_FUNCS, 4)])       # wide multi-output
+def test_wide_datasets_fall_back_to_fewer_datapoints_per_lane(native, orc, ref, pop, L, V, O, N, funcs, layers):
+    """Hundreds of inputs: 32*K datapoints x (V + O) floats must fit shared memory, so K drops to 4 / 1 instead of
+    the call failing (the reference accepts var_len <= 512, forward.cu:318-324)."""
+    v, t, s = make_forest(orc, pop, L, V, O, funcs, layers, keys=(23, 9), consts=(-1.0, 0.5, 2.0))
+    X, y = make_data(N, V, O, seed=8)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    got = G.abi_sr_fitness(native, dv, dt, ds, dX, dy, True)
+    want = ref.sr_fitness(dv, dt, ds, dX, dy, True, kernel_type=4)
+    torch.cuda.synchronize()
+    G.assert_close_fitness(got, want, rtol=RTOL, what=f"wide dataset V={V} O={O}")
+    vars_used = v[(t & 0x7F) == 0]
+    assert vars_used.max() >= V // 2      # the trees do read far columns
+
+
+@pytest.mark.parametrize("V,N", [(10, 100000), (20, 70000)])
+def test_more_than_64_datapoint_tiles(native, orc, V, N):
+    """N far beyond 64 tiles of the staging area (the ticket words are reused round-robin): compared with the CPU
+    oracle on exact ops, and with the mean of chunk-wise fitness (linearity of the error sum)."""
+    pop, L = 64, 64
+    v, t, s = make_forest(orc, pop, L, V, 1, EXACT_FUNCS, 4, keys=(3, 30))
+    X, y = make_data(N, V, 1, seed=12)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    got = G.abi_sr_fitness(native, dv, dt, ds, dX, dy, True)
+    torch.cuda.synchronize()
+    want = orc.sr_fitness(v, t, s, X, y, nthreads=8)
+    G.assert_close_fitness(got, want, rtol=1e-4, what=f"{N} datapoints")
+    half = N // 2
+    a = G.abi_sr_fitness(native, dv, dt, ds, dX[:half].contiguous(), dy[:half].contiguous(), True)
+    b = G.abi_sr_fitness(native, dv, dt, ds, dX[half:].contiguous(), dy[half:].contiguous(), True)
+    torch.cuda.synchronize()
+    comb = (a.double() * half + b.double() * (N - half)) / N
+    G.assert_close_fitness(got, comb.float(), rtol=1e-4, what="chunk linearity")
+
+
 # --------------------------------------------------------------------------- edge cases
 def _chain_forest(L, kind):
     """Degenerate shapes: 'unary' = neg(neg(...x0)), 'left' = ((x0+x1)+x1)+..., 'right' = x0+(x1+(x1+...)),
