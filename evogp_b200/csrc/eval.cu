@@ -25,6 +25,7 @@
 //        fused into the final store (Scatter: peer-mapped buffers over NVLink).
 #include <cstdlib>
 #include "lower.cuh"
+#include "lower_fast.cuh"
 #include "fastpath_k8.inc"
 #include "fastpath_k8_tmem.inc"
 #include "fastpath_k16_tmem.inc"
@@ -500,6 +501,8 @@ static thread_local int g_sm_count = 0, g_max_smem = 0, g_smem_per_sm = 0;
 static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_STACK"); return !(e && e[0] == '0'); }();
 // EVOGP_K16_SPLIT=1 feeds the K = 16 kernel split-mode programs (lower.cuh; the A/B switch of profiles/; default off)
 static const bool g_k16_split = []() { const char *e = getenv("EVOGP_K16_SPLIT"); return e && e[0] == '1'; }();
+// EVOGP_FOLD=0 lowers without constant folding (the A/B switch of profiles/; default on)
+static const bool g_fold = []() { const char *e = getenv("EVOGP_FOLD"); return !(e && e[0] == '0'); }();
 static const int g_force_k = []() { const char *e = getenv("EVOGP_REPLAY_K"); return e ? atoi(e) : 0; }();
 // optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
@@ -549,6 +552,7 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
     a.rows_have_sizes = len_stride != 1;
     a.deep_from = deep_from;
+    a.fold = g_fold ? 1 : 0;
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
     static thread_local int per_sm_cached = 0, per_sm_dev = -1;
@@ -567,6 +571,38 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     count_launch();
     return check_launch("lower_kernel");
 }
+// EVOGP_LOWER_FAST=0 keeps every row on the generic pass (the A/B switch of profiles/; default on)
+static const bool g_lower_fast = []() { const char *e = getenv("EVOGP_LOWER_FAST"); return !(e && e[0] == '0'); }();
+
+// the register-resident pass of lower_fast.cuh: single-output, max_tree_len <= 64, packed size rows
+template <int NSETS>
+static int launch_lower_fast(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
+                             const int16_t *type, const int16_t *size, int depth, int deep_from, cudaStream_t st) {
+    auto kern = lower_fast_kernel<NSETS>;
+    const int warps = 8;
+    const size_t smem = warps * lower_fast_per_warp<NSETS>((int)L);
+    LowerArgs a;
+    a.value = value; a.type = type; a.size = size;
+    a.prog = w.prog; a.sched = w.sched;
+    a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
+    a.rows_have_sizes = 1;
+    a.deep_from = deep_from;
+    a.fold = g_fold ? 1 : 0;
+    static thread_local int per_sm_cached = 0, per_sm_dev = -1;
+    if (per_sm_dev != g_props_dev * 4 + NSETS) {
+        int n = 0;
+        EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem));
+        per_sm_cached = n < 1 ? 1 : n;
+        per_sm_dev = g_props_dev * 4 + NSETS;
+    }
+    long long grid = ((long long)P + warps - 1) / warps;
+    const long long cap = (long long)g_sm_count * per_sm_cached;       // one resident wave, grid-stride (as lower_kernel)
+    if (grid > cap) grid = cap;
+    kern<<<(unsigned)grid, warps * 32, smem, st>>>(a);
+    count_launch();
+    return check_launch("lower_fast_kernel");
+}
+
 // split: single-output programs for the K = 16 replay kernel (LOAD + acc-form for operators on leaves)
 template <bool MULTI>
 static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
@@ -574,6 +610,9 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
                         cudaStream_t st) {
     if constexpr (!MULTI) {
         if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
+        if (g_lower_fast && len_stride != 1 && L <= 64)
+            return L <= 32 ? launch_lower_fast<1>(w, P, L, V, O, value, type, size, depth, deep_from, st)
+                           : launch_lower_fast<2>(w, P, L, V, O, value, type, size, depth, deep_from, st);
     }
     return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
 }
@@ -794,6 +833,34 @@ int evogp_sr_fitness_compact_len(unsigned popSize, unsigned dataPoints, unsigned
                                  size_t workspace_bytes, void *stream) {
     return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type, lengths, 1,
                     variables, labels, fitnesses, workspace, workspace_bytes, stream);
+}
+
+// Diagnostics: run only the lowering pass and hand back the programs (tests compare the fast and the generic pass).
+extern "C" int evogp_debug_lower(unsigned popSize, unsigned gpLen, unsigned varLen, unsigned outLen, const float *value,
+                                 const int16_t *type, const int16_t *subtree_size, int use_fast, int deep_from,
+                                 void *workspace, size_t workspace_bytes, unsigned long long *programs, void *stream) {
+    EVOGP_REQUIRE(popSize > 0 && gpLen > 0 && gpLen <= (unsigned)kMaxStack && varLen > 0 && outLen > 0, "bad shape");
+    if (workspace_bytes < evogp_eval_workspace_bytes(popSize, gpLen) || workspace == nullptr) {
+        set_error("workspace too small");
+        return EVOGP_ERR_WORKSPACE;
+    }
+    int rc = ensure_device_ok();
+    if (rc) return rc;
+    rc = device_props();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Workspace w = carve(workspace, popSize, gpLen);
+    const int depth = stack_depth_bound((int)gpLen);
+    const int df = deep_from > 0 ? deep_from : kNoDeepSlots;
+    EVOGP_CUDA(cudaMemsetAsync(w.prog, 0, prog_bytes(popSize, gpLen), st));
+    if (outLen > 1) rc = launch_lower_t<true, false>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, depth, kNoDeepSlots, st);
+    else if (use_fast && gpLen <= 64)
+        rc = gpLen <= 32 ? launch_lower_fast<1>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, depth, df, st)
+                         : launch_lower_fast<2>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, depth, df, st);
+    else rc = launch_lower_t<false, false>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, depth, df, st);
+    if (rc) return rc;
+    EVOGP_CUDA(cudaMemcpyAsync(programs, w.prog, prog_bytes(popSize, gpLen), cudaMemcpyDeviceToDevice, st));
+    return EVOGP_OK;
 }
 
 extern "C" void evogp_eval_set_timing_events(void *begin_event, void *end_event) {

@@ -240,6 +240,37 @@ __host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
 #endif
 }
 
+// ---- constant folding (one level): a function whose operands are all constant LEAVES is itself a constant.  The
+// value is computed by the very operator the replay kernels would run per datapoint (program.cuh, same translation
+// unit, same -use_fast_math lowering), so every downstream value keeps its bits; the node then reads as a constant
+// leaf - an operand of its father - and its instructions disappear from the program (BASELINE configs[1]: 13.9 -> 11.1
+// instructions per tree).  Host builds (tests/host_lower_harness.cu) supply the oracle's operators instead.
+#ifdef __CUDA_ARCH__
+__device__ inline float fold_unary(int u, float a) {
+#define EVOGP_FU(n) case n: return unary_op<n>(a);
+    switch (u) {
+        EVOGP_FU(0) EVOGP_FU(1) EVOGP_FU(2) EVOGP_FU(3) EVOGP_FU(4) EVOGP_FU(5) EVOGP_FU(6) EVOGP_FU(7)
+        EVOGP_FU(8) EVOGP_FU(9) EVOGP_FU(10) EVOGP_FU(11) EVOGP_FU(12) EVOGP_FU(13) EVOGP_FU(14)
+    default: return 0.0f;
+    }
+#undef EVOGP_FU
+}
+__device__ inline float fold_binary(int b, float x, float y) {
+#define EVOGP_FB(n) case n: return binary_op<n>(x, y);
+    switch (b) {
+        EVOGP_FB(0) EVOGP_FB(1) EVOGP_FB(2) EVOGP_FB(3) EVOGP_FB(4) EVOGP_FB(5) EVOGP_FB(6)
+        EVOGP_FB(7) EVOGP_FB(8) EVOGP_FB(9) EVOGP_FB(10) EVOGP_FB(11) EVOGP_FB(12)
+    default: return 0.0f;
+    }
+#undef EVOGP_FB
+}
+#else
+extern "C" float evogp_host_fold_unary(int u, float a);            // provided by the host harness (oracle operators)
+extern "C" float evogp_host_fold_binary(int b, float x, float y);
+inline float fold_unary(int u, float a) { return evogp_host_fold_unary(u, a); }
+inline float fold_binary(int b, float x, float y) { return evogp_host_fold_binary(b, x, y); }
+#endif
+
 // Stage the row into k.t / k.v / k.s.  Returns false when the length is impossible.
 // val == nullptr: the rows are already staged in k.t / k.v (/ k.s).
 // size == nullptr with val != nullptr, or have_sizes == false: no size row; sizes are recomputed from the arities.
@@ -316,7 +347,7 @@ __host__ __device__ inline void emit_nan(Lanes ln, uint2 *out, int Lp) {
 template <bool split>
 __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, const int16_t *typ, const int16_t *size,
                                                  int len, int L, int Lp, int V, int depth_budget, uint2 *out,
-                                                 LowerScratch k, bool have_sizes, int deep_from) {
+                                                 LowerScratch k, bool have_sizes, int deep_from, bool fold) {
     // split: operators on leaves only are emitted as LOAD + acc-form instead of the fresh-value forms
     // (UV/UK/VV/VK/KV), so programs use 6 operand forms per operator instead of 9 - the K = 16 replay kernel
     // keeps only those laid out (its bodies are twice as long; the instruction cache is its limit)
@@ -333,40 +364,69 @@ __host__ __device__ inline int lower_tree_single(Lanes ln, const float *val, con
         bool bad = false;
         for (int i = ln.lane; i < len; i += ln.n) {
             const int ar = arity_of(k.t[i], false);
-            int c[3], tot = 1, pos = i + 1;
+            int tot = 1, pos = i + 1;
             bool mine = false;
             for (int a = 0; a < ar; ++a) {
                 if (pos >= len) { mine = true; break; }
                 const int cs = k.s[pos];
                 if (cs < 1) { mine = true; break; }
-                c[a] = pos;
                 tot += cs;
                 pos += cs;
             }
             if ((int)k.s[i] != tot || i + tot > len) mine = true;
-            int m = 0;
-            if (!mine) {
-                if (ar == 1) m = (split && !is_func(c[0])) ? 2 : 1;
-                else if (ar == 2)    // two constants (or split): LOAD + AK / AV
-                    m = (!is_func(c[0]) && !is_func(c[1]) && (split || (is_const(c[0]) && is_const(c[1])))) ? 2 : 1;
-                else if (ar == 3)    // every leaf child is a LOAD
-                    m = 1 + (!is_func(c[0])) + (!is_func(c[1])) + (!is_func(c[2]));
-            }
             bad |= mine;
-            k.M[i] = (uint16_t)m;
-            k.q[i] = 0;
-            k.D[i] = 0;
         }
-        if (ln.lane == 0) {
-            k.D[len] = 0;
-            if ((int)k.s[0] != len) bad = true;
-        }
+        if (ln.lane == 0 && (int)k.s[0] != len) bad = true;
         if (!lanes_any(bad)) break;
         if (attempt || !fix_sizes<false>(ln, len, k)) {
             emit_nan(ln, out, Lp);
             return -1;
         }
     }
+    // ---- constant folding, one level (decide from the untouched row, then apply): the folded node keeps its size, so
+    //      every child position (i + 1, c + size[c]) stays valid; its former children are dead slots nobody visits ----
+    if (fold) {
+        for (int i = ln.lane; i < len; i += ln.n) {
+            const int ar = arity_of(k.t[i], false);
+            bool can = false;
+            uint32_t fv = 0;
+            if (ar == 1 || ar == 2) {
+                const int x = i + 1, y = x + k.s[x];
+                const unsigned func = f32_to_u32(bits_f32(k.v[i]));
+                if (ar == 1 && k.t[x] == NT_CONST) {
+                    can = true;
+                    fv = f32_bits(fold_unary(unary_slot(func), bits_f32(k.v[x])));
+                } else if (ar == 2 && k.t[x] == NT_CONST && k.t[y] == NT_CONST) {
+                    can = true;
+                    fv = f32_bits(fold_binary(binary_slot(func), bits_f32(k.v[x]), bits_f32(k.v[y])));
+                }
+            }
+            k.q[i] = can ? 1 : 0;
+            k.D[i] = fv;
+        }
+        lanes_sync();
+        for (int i = ln.lane; i < len; i += ln.n)
+            if (k.q[i]) { k.t[i] = NT_CONST; k.v[i] = k.D[i]; }
+        lanes_sync();
+    }
+    // ---- mark the instruction slots each node contributes itself ----
+    for (int i = ln.lane; i < len; i += ln.n) {
+        const int ar = arity_of(k.t[i], false);
+        int m = 0;
+        if (ar == 1) {
+            m = (split && !is_func(i + 1)) ? 2 : 1;
+        } else if (ar == 2) {   // two constants (or split): LOAD + AK / AV
+            const int x = i + 1, y = x + k.s[x];
+            m = (!is_func(x) && !is_func(y) && (split || (is_const(x) && is_const(y)))) ? 2 : 1;
+        } else if (ar == 3) {   // every leaf child is a LOAD
+            const int a = i + 1, b = a + k.s[a], c = b + k.s[b];
+            m = 1 + (!is_func(a)) + (!is_func(b)) + (!is_func(c));
+        }
+        k.M[i] = (uint16_t)m;
+        k.q[i] = 0;
+        k.D[i] = 0;
+    }
+    if (ln.lane == 0) k.D[len] = 0;
     if (!is_func(0)) {   // the tree is a single leaf
         if (ln.lane == 0) {
             out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of(k.t[0], bits_f32(k.v[0]), V), 0);
@@ -565,10 +625,10 @@ __host__ __device__ inline int lower_tree_multi(Lanes ln, const float *val, cons
 template <bool MULTI, bool SPLIT = false>
 __host__ __device__ inline int lower_tree(Lanes ln, const float *val, const int16_t *typ, const int16_t *size, int len,
                                           int L, int Lp, int V, int O, int depth_budget, uint2 *out, LowerScratch k,
-                                          bool have_sizes = true, int deep_from = kNoDeepSlots) {
+                                          bool have_sizes = true, int deep_from = kNoDeepSlots, bool fold = true) {
     if (MULTI) return lower_tree_multi(ln, val, typ, size, len, L, Lp, V, O, out, k, have_sizes);
     return lower_tree_single<SPLIT>(ln, val, typ, size, len, L, Lp, V, depth_budget, out, k, have_sizes,
-                                    deep_from);
+                                    deep_from, fold);
 }
 
 #ifdef __CUDACC__
@@ -580,6 +640,7 @@ struct LowerArgs {
     unsigned *sched;          // 64 scheduler words, zeroed here (the replay kernel runs after this one)
     int P, L, Lp, V, O, depth_budget, rows_have_sizes;
     int deep_from;            // SPLIT: slots >= deep_from are addressed with the deep opcodes (program.cuh); else kNoDeepSlots
+    int fold;                 // single-output: fold functions of constant leaves into constants
 };
 
 // one warp per tree, grid-stride over the population
@@ -597,7 +658,7 @@ __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
         const int16_t *srow = g.rows_have_sizes ? g.size + (size_t)n * g.L : nullptr;
         const int len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
         lower_tree<MULTI, SPLIT>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
-                          g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0, g.deep_from);
+                          g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0, g.deep_from, g.fold != 0);
         __syncwarp();
     }
 }

@@ -47,7 +47,11 @@ constexpr int I_PUSH_SHIFT = 9;
 constexpr uint32_t I_PUSH_MASK = 0xFu << I_PUSH_SHIFT;
 constexpr uint32_t I_OUT = 1u << 9;                                                  // multi-output programs
 constexpr uint32_t I_IF3_ACONST = 1u << 10, I_IF3_BCONST = 1u << 11, I_IF3_CCONST = 1u << 12;
+#ifdef EVOGP_IDXA_TOP   // A/B layout: idxA in the top ten bits (one shift extracts it), idxB below it
+constexpr int I_IDXA_SHIFT = 22, I_IDXB_SHIFT = 13;
+#else
 constexpr int I_IDXA_SHIFT = 13, I_IDXB_SHIFT = 23;
+#endif
 constexpr uint32_t I_IDXA_MASK = 0x3FFu, I_IDXB_MASK = 0x1FFu;
 // (Operand-stack slots held in registers were measured and rejected: profiles/r1_replay_v3_regbanks.txt - 45 %
 // fewer shared-memory wavefronts but 25 more registers and MOV work per save, 479 us vs 309 us.)

@@ -82,6 +82,14 @@ size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen);
  * lowering pass).  Pass NULLs to switch it off. */
 void evogp_eval_set_timing_events(void *begin_event, void *end_event);
 
+/* Diagnostics: run only the lowering pass (packed rows -> accumulator-machine programs) and copy the
+ * programs out: programs = DEVICE u64[popSize][(maxGPLen + 2) & ~1].  use_fast: 1 = the register-resident pass where it
+ * applies (single-output, maxGPLen <= 64), 0 = the generic pass.  deep_from: operand-stack slots >= deep_from are marked
+ * with the deep opcodes (0 = none).  The two passes must produce identical programs (tests/test_gpu_lowering.py). */
+int evogp_debug_lower(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
+                      const int16_t *type, const int16_t *subtree_size, int use_fast, int deep_from, void *workspace,
+                      size_t workspace_bytes, unsigned long long *programs, void *stream);
+
 /* replaces evaluate(), kernel.h:71-81 (forward.cu:353-371): tree n on variables[n, :] -> results[n, :outLen]. */
 int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,
                    const int16_t *type, const int16_t *subtree_size, const float *variables, float *results,

@@ -14,20 +14,23 @@
 
 extern "C" float oracle_apply_unary(unsigned f, float a);
 extern "C" float oracle_apply_binary(unsigned f, float a, float b);
+// constant folding in the lowering pass uses the interpreter's own operators (on the GPU: program.cuh's; here: the oracle's)
+extern "C" float evogp_host_fold_unary(int u, float a) { return u < 15 ? oracle_apply_unary((unsigned)u + 14u, a) : 0.0f; }
+extern "C" float evogp_host_fold_binary(int b, float x, float y) { return b < 13 ? oracle_apply_binary((unsigned)b + 1u, x, y) : 0.0f; }
 
 using namespace evogp;
 
 template <bool MULTI>
 static int run_row(const float *val, const int16_t *typ, const int16_t *size, int len, int L, int V, int O, const float *X,
                    int N, float *out, int *need_out, int *ninstr_out, int *maxsp_out, bool split = false,
-                   int deep_from = kNoDeepSlots) {
+                   int deep_from = kNoDeepSlots, bool fold = true) {
     const int Lp = (L + 2) & ~1;   // prog_pitch(): one spare slot so C_END always fits
     std::vector<uint2> prog(Lp);
     std::vector<unsigned char> mem(lower_scratch_bytes(L) + 64);
     const LowerScratch scratch = carve_scratch(mem.data(), L);
     const int budget = stack_depth_bound(L);
-    const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from)
-                           : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from);
+    const int need = split ? lower_tree<MULTI, true>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from, fold)
+                           : lower_tree<MULTI, false>(Lanes{0, 1}, val, typ, size, len, L, Lp, V, O, budget, prog.data(), scratch, true, deep_from, fold);
     *need_out = need;
     int ninstr = 0;
     while (ninstr < Lp && (prog[ninstr].x & I_CODE_MASK) != C_END) ++ninstr;
@@ -137,10 +140,11 @@ extern "C" int harness_batch_forward(int P, int N, int L, int V, int O, const fl
         const int16_t *srow = (use_sizes & 1) ? size + (size_t)n * L : nullptr;
         const bool split = (use_sizes & 2) != 0;
         const int deep_from = (use_sizes & 4) ? 1 : kNoDeepSlots;   // bit 2: slots >= 1 are deep (exercises the deep opcodes)
+        const bool fold = !(use_sizes & 8);                         // bit 3: lower without constant folding
         if (O > 1) rc = run_row<true>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from);
+                                      out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from, fold);
         else rc = run_row<false>(value + (size_t)n * L, type + (size_t)n * L, srow, len, L, V, O, X, N,
-                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from);
+                                 out + (size_t)n * N * O, need + n, ninstr + n, maxsp + n, split, deep_from, fold);
         if (rc) return rc * 1000000 - n;
     }
     return 0;

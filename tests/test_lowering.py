@@ -173,3 +173,22 @@ def test_sizes_are_verified_not_trusted(harness, orc):
     assert same(got_stale, want)
     got_ref, need2, *_ = run(harness, v, t, s, X, 1)
     assert np.array_equal(need0, need2) and np.array_equal(need1, need2)
+
+
+@pytest.mark.parametrize("funcs,const_prob", [(ARITH_FUNCS, 0.5), (ALL_FUNCS, 0.8), (ARITH_FUNCS + ["neg", "sin"], 1.0)])
+def test_constant_folding_changes_the_program_not_the_values(harness, orc, funcs, const_prob):
+    """A function of constant leaves is folded at lowering time with the interpreter's own operator: fewer
+    instructions, the same bits (also with all-constant trees, which fold level by level only once)."""
+    layers = 4 if "if" in funcs else 6
+    v, t, s = make_forest(orc, 3000, 64, 3, 1, funcs, layers, keys=(41, 42), consts=(-1.0, 0.0, 0.5, 2.0), const_prob=const_prob)
+    X, _ = make_data(21, 3, seed=11)
+    want = orc.batch_forward(v, t, s, X, 1)
+    got_f, need_f, ninstr_f, _ = run(harness, v, t, s, X, 1, use_sizes=1)
+    got_n, need_n, ninstr_n, _ = run(harness, v, t, s, X, 1, use_sizes=1 | 8)
+    assert same(got_f, want) and same(got_n, want)
+    assert (ninstr_f <= ninstr_n).all() and ninstr_f.sum() < 0.95 * ninstr_n.sum()
+    assert (need_f <= need_n).all()
+    # the other emission modes see the folded row too
+    for flags in (3, 5, 7):
+        got_m, *_ = run(harness, v, t, s, X, 1, use_sizes=flags)
+        assert same(got_m, want)
