@@ -45,7 +45,12 @@ def main():
     N, V = 256, 3
     X = torch.rand(N, V, device="cuda") * 4 - 2
     y = (X[:, :1] ** 2 * 0.5 + X[:, 1:2] * X[:, 2:3] - 1.0).contiguous()
-    problem = SymbolicRegression(datapoints=X, labels=y)
+    problem = SymbolicRegression(datapoints=X, labels=y)                      # fitness from the SR-fitness kernel (tree_SR_fitness)
+    # Selection is driven by the reference's own "torch" mode (symbolic_regression.py:73-81: Forest.batch_forward ->
+    # tree_evaluate per (tree, datapoint), reduced by torch): per-tree OUTPUTS are bit-identical under both operator
+    # libraries, so both runs sort identical numbers.  (Kernel fitness differs in the last bits by summation order -
+    # inside 1e-5, but enough to flip a near-tie in torch.sort and send the two runs down different histories.)
+    selector = SymbolicRegression(datapoints=X, labels=y, execute_mode="torch")
     desc = rt.GenerateDescriptor(max_tree_len=64, input_len=V, output_len=1, using_funcs=["+", "-", "*", "/", "sin", "neg"],
                                  max_layer_cnt=5, const_samples=[-1, 0, 1, 0.5])
     algo = GeneticProgramming(initial_forest=rt.Forest.random_generate(pop_size=pop, descriptor=desc),
@@ -56,14 +61,16 @@ def main():
     for g in range(gens):
         f = algo.forest
         fit = problem.evaluate(f)
+        sel = selector.evaluate(f)
         lens = f.batch_subtree_size[:, 0].long()
         valid = (torch.arange(f.max_tree_len, device="cuda")[None, :] < lens[:, None])
         dump[f"value{g}"] = torch.where(valid, f.batch_node_value, torch.zeros_like(f.batch_node_value)).cpu().numpy()
         dump[f"type{g}"] = torch.where(valid, f.batch_node_type, torch.zeros_like(f.batch_node_type)).cpu().numpy()
         dump[f"size{g}"] = torch.where(valid, f.batch_subtree_size, torch.zeros_like(f.batch_subtree_size)).cpu().numpy()
         dump[f"fitness{g}"] = fit.cpu().numpy()
-        fit = torch.where(torch.isnan(fit), torch.full_like(fit, float("-inf")), fit)     # pipeline/standard.py:43
-        algo.step(fit)
+        dump[f"torch_fitness{g}"] = sel.cpu().numpy()
+        sel = torch.where(torch.isnan(sel), torch.full_like(sel, float("-inf")), sel)     # pipeline/standard.py:43
+        algo.step(sel)
     best = algo.forest[int(torch.argmax(torch.nan_to_num(problem.evaluate(algo.forest), nan=float("-inf"))))]
     dump["best_forward"] = best.forward(X).cpu().numpy()                     # Tree.forward -> tree_evaluate
     rows = X[torch.arange(algo.forest.pop_size, device="cuda") % N].contiguous()

@@ -56,6 +56,11 @@ def test_seeded_loop_is_identical_under_the_reference_front_end(runs):
             same = np.array_equal(a.view(np.uint32), b.view(np.uint32)) if a.dtype.kind == "f" else np.array_equal(a, b)
             assert same, f"generation {g}: node_{name} differs in {(a != b).any(1).sum()} of {a.shape[0]} trees"
         assert close(ours[f"fitness{g}"], ref[f"fitness{g}"]), f"generation {g}: fitness beyond 1e-5 relative"
+        # per-tree outputs (Forest.batch_forward -> tree_evaluate) carry the same bits under both libraries, so the torch-mode
+        # fitness that drives selection in both runs is identical, NaNs included
+        ta, tb = ref[f"torch_fitness{g}"], ours[f"torch_fitness{g}"]
+        assert np.array_equal(np.isnan(ta), np.isnan(tb)) and np.array_equal(ta[~np.isnan(ta)], tb[~np.isnan(tb)]), \
+            f"generation {g}: torch-mode fitness differs in {(ta != tb).sum()} trees"
 
 
 def test_forward_paths_and_pareto_front_agree(runs):
