@@ -20,7 +20,7 @@ _ops_loaded = False
 ABI_SYMBOLS = (
     "evogp_version", "evogp_last_error", "evogp_launch_count", "evogp_generate", "evogp_mutate", "evogp_crossover",
     "evogp_eval_workspace_bytes", "evogp_eval_set_timing_events", "evogp_evaluate", "evogp_SR_fitness", "evogp_batch_forward",
-    "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation", "evogp_SR_fitness_scatter", "evogp_debug_lower",
+    "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation", "evogp_SR_fitness_scatter", "evogp_debug_lower", "evogp_classification_accuracy",
 )
 
 
@@ -57,6 +57,8 @@ def abi():
     L.evogp_host_release.restype = None
     L.evogp_next_generation.restype = i
     L.evogp_next_generation.argtypes = [i, i, vp, vp, vp, vp, i, i, f, u, u, u, f, f, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.evogp_classification_accuracy.restype = i
+    L.evogp_classification_accuracy.argtypes = [u, u, u, u, u, vp, vp, vp, vp, vp, f, vp, vp, sz, vp]
     L.evogp_debug_lower.restype = i
     L.evogp_debug_lower.argtypes = [u, u, u, u, vp, vp, vp, i, i, vp, sz, vp, vp]
     L.evogp_eval_set_timing_events.restype = None

@@ -32,7 +32,12 @@
 
 namespace evogp {
 
-enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_OUTPUT = 2, MODE_ROWWISE = 3 };
+// MODE_ACC: classification accuracy (problem/classification.py:54-67) - per datapoint the predicted class (arg-max of the
+// outputs, or the rounded single output) is compared with the label inside the kernel; one float per tree leaves the SM.
+// MODE_R2: squared Pearson correlation of the single output with the label (problem/transformation.py:36-43).
+enum : int { MODE_MSE = 0, MODE_ABS = 1, MODE_ACC = 2, MODE_OUTPUT = 3, MODE_ROWWISE = 4 };
+__host__ __device__ inline bool is_reduce_mode(int mode) { return mode <= MODE_ACC; }            // one float per tree
+__host__ __device__ inline int label_columns(int mode, int O) { return mode <= MODE_ABS ? O : (mode == MODE_ACC ? 1 : 0); }
 
 // Fitness exchange fused into the evaluation kernel (multi-GPU): every tree's fitness is stored straight into each
 // rank's full-population buffer through peer-mapped memory (NVLink), at row_offset + tree.
@@ -43,7 +48,7 @@ struct Scatter {
 };
 int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value, const int16_t *type,
              const int16_t *size, int len_stride, const float *X, const float *labels, float *out, void *workspace,
-             size_t workspace_bytes, void *stream, Scatter scatter = Scatter());
+             size_t workspace_bytes, void *stream, Scatter scatter = Scatter(), float acc_half = 0.0f, float acc_max = 0.0f);
 
 
 
@@ -51,7 +56,8 @@ struct ReplayArgs {
     const uint2 *prog;      // [P][Lp]
     unsigned *sched;        // [0] ticket counter
     const float *X;         // MODE_ROWWISE: [P][V]; else [N][V]
-    const float *labels;    // [N][O] (loss modes)
+    const float *labels;    // [N][O] (loss modes); [N] class ids (MODE_ACC)
+    float acc_half, acc_max;   // MODE_ACC, single output: prediction = clamp(round(out + acc_half), 0, acc_max)
     float *out;             // fitness[P] | results[P][N][O] | results[P][O]
     int P, Lp, N, V, O;
     int NP;                 // N rounded up to a whole number of passes
@@ -171,7 +177,8 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
     // ---- shared memory carve-up ----
     float *Xs = reinterpret_cast<float *>(smem_raw);                    // [V][NP]   (not ROWWISE)
     float *Ys = Xs + (ROWWISE ? 0 : (size_t)g.V * g.NP);                // [O][NP]   (loss modes)
-    float *after = Ys + ((g.mode <= MODE_ABS) ? (size_t)g.O * g.NP : 0);
+    const int LC = label_columns(g.mode, g.O);
+    float *after = Ys + (size_t)LC * g.NP;
     uint2 *progs = reinterpret_cast<uint2 *>(after) + (size_t)warp * 2 * g.Lp;          // 2 rows / warp
     float *stacks = reinterpret_cast<float *>(reinterpret_cast<uint2 *>(after) + (size_t)nwarp * 2 * g.Lp);
     float *stack = stacks + (size_t)warp * g.smem_depth * SLOT;
@@ -186,10 +193,10 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
             const int d = idx / g.V, v = idx - d * g.V;
             Xs[v * g.NP + d] = d < g.N ? __ldg(g.X + idx) : 0.0f;
         }
-        if (g.mode <= MODE_ABS) {
-            const int tl = g.NP * g.O;
+        if (LC > 0) {
+            const int tl = g.NP * LC;
             for (int idx = threadIdx.x; idx < tl; idx += blockDim.x) {
-                const int d = idx / g.O, o = idx - d * g.O;
+                const int d = idx / LC, o = idx - d * LC;
                 Ys[o * g.NP + d] = d < g.N ? __ldg(g.labels + idx) : 0.0f;
             }
         }
@@ -414,7 +421,35 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
             }
 
             // ---- per-pass epilogue ----
-            if (g.mode <= MODE_ABS) {
+            if (g.mode == MODE_ACC) {
+                float lab[K];
+                ld_vec<K>(lab, Ys + pass_off + lane_off);
+                if constexpr (MULTI) {
+                    // arg-max of softmax(outputs) as torch computes it (classification.py:62-64): softmax is monotone, so
+                    // the first maximal output wins; a NaN or an infinite maximum makes every probability NaN -> class 0
+                    float best[K], cls[K];
+                    bool poison[K];
+                    ld_vec<K>(best, outs + lane_off);
+                    FOR_K { cls[k] = 0.0f; poison[k] = !(best[k] == best[k]); }
+                    for (int o = 1; o < g.O; ++o) {
+                        float r[K];
+                        ld_vec<K>(r, outs + o * SLOT + lane_off);
+                        FOR_K {
+                            poison[k] = poison[k] || !(r[k] == r[k]);
+                            if (r[k] > best[k]) { best[k] = r[k]; cls[k] = (float)o; }
+                        }
+                    }
+                    FOR_K {
+                        const float pred = (poison[k] || fabsf(best[k]) == __int_as_float(0x7f800000)) ? 0.0f : cls[k];
+                        if (pass_off + dp_index<K>(lane, k) < g.N && pred == lab[k]) err += 1.0f;
+                    }
+                } else {
+                    FOR_K {   // transform(): clamp(round(out + max / 2), 0, max), round half to even (classification.py:51-52)
+                        const float p = fminf(fmaxf(rintf(acc[k] + g.acc_half), 0.0f), g.acc_max);
+                        if (pass_off + dp_index<K>(lane, k) < g.N && acc[k] == acc[k] && p == lab[k]) err += 1.0f;
+                    }
+                }
+            } else if (g.mode <= MODE_ABS) {
                 if constexpr (MULTI) {
                     for (int o = 0; o < g.O; ++o) {
                         float y[K], r[K];
@@ -463,7 +498,7 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
                 }
             }
         }
-        if (g.mode <= MODE_ABS) {
+        if (is_reduce_mode(g.mode)) {
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) err += __shfl_xor_sync(0xffffffffu, err, s);
             if (!g.first_tile) {                                              // running sum of the earlier tiles:
@@ -671,7 +706,7 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
     a.tmem_cols = 0;
     auto per_warp = [&]() { return (size_t)2 * a.Lp * 8 + (size_t)a.smem_depth * SLOT * 4 + (MULTI ? (size_t)a.O * SLOT * 4 : 0) + 16; };
     // the dataset slice a launch stages: all of it when it fits next to >= 4 warps, else whole passes of it
-    const size_t per_dp = ROWWISE ? 0 : ((size_t)a.V + (a.mode <= MODE_ABS ? a.O : 0)) * 4;   // bytes per datapoint
+    const size_t per_dp = ROWWISE ? 0 : ((size_t)a.V + label_columns(a.mode, a.O)) * 4;   // bytes per datapoint
     const int N_total = a.N;
     int tile = a.NP;                                                                         // datapoints per launch
     // one launch when the dataset leaves room for two 8-warp CTAs per SM; otherwise tiles of <= 48 KB of dataset so
@@ -696,7 +731,7 @@ static int launch_replay_t(ReplayArgs a, int depth, cudaStream_t st) {
         a.NP = a.npass * SLOT;
         a.d_base = d0; a.N_total = N_total; a.first_tile = d0 == 0; a.last_tile = d0 + tile >= N_total;
         if (!ROWWISE) a.X = X0 + (size_t)d0 * a.V;
-        if (Y0) a.labels = Y0 + (size_t)d0 * a.O;
+        if (Y0) a.labels = Y0 + (size_t)d0 * label_columns(a.mode, a.O);
         // one ticket counter per launch: the 64 words lower_kernel zeroed, reused round-robin (launches are ordered
         // on the stream, so word t % 64 is idle again by the time launch t is enqueued)
         a.sched = sched0 + (t & 63);
@@ -788,9 +823,9 @@ static int launch_replay(const ReplayArgs &a, int depth, ReplayChoice c, cudaStr
 
 int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned O, const float *value,
              const int16_t *type, const int16_t *size, int len_stride, const float *X, const float *labels, float *out,
-             void *workspace, size_t workspace_bytes, void *stream, Scatter scatter) {
+             void *workspace, size_t workspace_bytes, void *stream, Scatter scatter, float acc_half, float acc_max) {
     EVOGP_REQUIRE(P > 0, "popSize must be larger than 0, got %u", P);
-    EVOGP_REQUIRE(scatter.peers == nullptr || (scatter.world >= 1 && scatter.world <= 32 && mode <= MODE_ABS),
+    EVOGP_REQUIRE(scatter.peers == nullptr || (scatter.world >= 1 && scatter.world <= 32 && is_reduce_mode(mode)),
                   "fitness scatter: world must be in [1, 32] (got %d) and the mode a loss mode", scatter.world);
     EVOGP_REQUIRE(L > 0 && L <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, L);
     EVOGP_REQUIRE(V > 0 && V <= 512, "var_len must be in (0, 512], got %u", V);   // forward.cu:320 asserts the same bound
@@ -809,7 +844,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     const Workspace w = carve(workspace, P, L);
     const int depth = stack_depth_bound((int)L);
     const bool multi = O > 1;
-    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth, prog_pitch(L), (int)O, ((size_t)V + (mode <= MODE_ABS ? O : 0)) * 4);
+    const ReplayChoice choice = choose_replay(multi, mode, (int)N, depth, prog_pitch(L), (int)O, ((size_t)V + label_columns(mode, (int)O)) * 4);
     const int deep_from = choice.K == 16 ? kTmemSlots16 : kNoDeepSlots;
     rc = multi ? launch_lower<true>(w, P, L, V, O, value, type, size, len_stride, depth, false, kNoDeepSlots, st)
                : launch_lower<false>(w, P, L, V, O, value, type, size, len_stride, depth, choice.K == 16 && g_k16_split, deep_from, st);
@@ -819,6 +854,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     a.P = (int)P; a.Lp = prog_pitch(L); a.N = (int)N; a.V = (int)V; a.O = (int)O;
     a.NP = 0; a.npass = 0; a.depth = depth; a.mode = mode;
     a.peers = scatter.peers; a.world = scatter.world; a.row_offset = scatter.row_offset;
+    a.acc_half = acc_half; a.acc_max = acc_max;
     return multi ? launch_replay<true>(a, depth, choice, st) : launch_replay<false>(a, depth, choice, st);
 }
 
@@ -898,6 +934,16 @@ extern "C" int evogp_SR_fitness_scatter(unsigned popSize, unsigned dataPoints, u
     sc.peers = peer_fitnesses; sc.world = (int)world; sc.row_offset = row_offset;
     return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
                     subtree_size, (int)gpLen, variables, labels, fitnesses, workspace, workspace_bytes, stream, sc);
+}
+
+extern "C" int evogp_classification_accuracy(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,
+                                             unsigned outLen, const float *value, const int16_t *type,
+                                             const int16_t *subtree_size, const float *variables, const float *class_labels,
+                                             float max_class, float *accuracy, void *workspace, size_t workspace_bytes,
+                                             void *stream) {
+    EVOGP_REQUIRE(max_class >= 0.0f, "max_class must be non-negative, got %f", max_class);
+    return run_eval(MODE_ACC, popSize, dataPoints, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, variables,
+                    class_labels, accuracy, workspace, workspace_bytes, stream, Scatter(), max_class / 2, max_class);
 }
 
 extern "C" int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen,

@@ -181,6 +181,26 @@ Tensor tree_batch_forward(int64_t pop_size, int64_t data_points, int64_t gp_len,
     return results;
 }
 
+Tensor tree_classification_accuracy(int64_t pop_size, int64_t data_points, int64_t gp_len, int64_t var_len, int64_t out_len,
+                                    Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor class_labels,
+                                    double max_class) {
+    check_forest_args(pop_size, gp_len, var_len, out_len, value, node_type, subtree_size);
+    TORCH_CHECK(data_points > 0, "data_points must larger than 0, but got ", data_points);
+    check_tensor(variables, {data_points, var_len}, at::kFloat, "variables");
+    check_tensor(class_labels, {data_points}, at::kFloat, "class_labels");
+    c10::cuda::CUDAGuard guard(value.device());
+    auto accuracy = at::empty({pop_size}, value.options());
+    size_t wsb = 0;
+    auto ws = eval_workspace(pop_size, gp_len, value, wsb);
+    check_rc(evogp_classification_accuracy((unsigned)pop_size, (unsigned)data_points, (unsigned)gp_len, (unsigned)var_len,
+                                           (unsigned)out_len, value.data_ptr<float>(), node_type.data_ptr<int16_t>(),
+                                           subtree_size.data_ptr<int16_t>(), variables.data_ptr<float>(),
+                                           class_labels.data_ptr<float>(), (float)max_class, accuracy.data_ptr<float>(),
+                                           ws.data_ptr(), wsb, cur_stream(value)),
+             "tree_classification_accuracy");
+    return accuracy;
+}
+
 Tensor3 tree_next_generation(int64_t pop_size, int64_t gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor order,
                              int64_t elite_cnt, int64_t survivor_cnt, double mutation_rate, int64_t var_len, int64_t out_len,
                              double out_prob, double const_prob, Tensor depth2leaf_probs, Tensor roulette_funcs,
@@ -216,6 +236,7 @@ TORCH_LIBRARY(evogp_cuda, m) {
     m.def("tree_evaluate(int pop_size, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
     m.def("tree_SR_fitness(int pop_size, int data_points, int gp_len, int var_len, int out_len, bool useMSE, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor labels, int kernel_type) -> Tensor");
     m.def("tree_next_generation(int pop_size, int gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor order, int elite_cnt, int survivor_cnt, float mutation_rate, int var_len, int out_len, float out_prob, float const_prob, Tensor depth2leaf_probs, Tensor roulette_funcs, Tensor const_samples, Tensor keys) -> (Tensor, Tensor, Tensor)");
+    m.def("tree_classification_accuracy(int pop_size, int data_points, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor class_labels, float max_class) -> Tensor");
     m.def("tree_batch_forward(int pop_size, int data_points, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
 }
 
@@ -226,5 +247,6 @@ TORCH_LIBRARY_IMPL(evogp_cuda, CUDA, m) {
     m.impl("tree_evaluate", &tree_evaluate);
     m.impl("tree_SR_fitness", &tree_SR_fitness);
     m.impl("tree_batch_forward", &tree_batch_forward);
+    m.impl("tree_classification_accuracy", &tree_classification_accuracy);
     m.impl("tree_next_generation", &tree_next_generation);
 }

@@ -1,5 +1,7 @@
 """Classification — fitness = accuracy of the forest's outputs on a labelled dataset
-(reference: src/evogp/problem/classification.py:11-83), on the fused batch_forward."""
+(reference: src/evogp/problem/classification.py:11-83).  The reference evaluates batch_forward ([P, N, O], by
+replicating the forest N times) and reduces it with torch softmax / argmax; here the prediction and the comparison with
+the label happen inside the evaluation kernel (`tree_classification_accuracy`) and one float per tree comes back."""
 from typing import Optional
 
 import torch
@@ -37,6 +39,18 @@ class Classification(BaseProblem):
         return torch.clamp(torch.round(x + self.maximum / 2), 0, self.maximum).squeeze(-1)
 
     def evaluate(self, forest: Forest):
+        f = forest
+        dev = f.batch_node_value.device
+        X = self.datapoints.to(dev, torch.float32).contiguous()
+        y = self.labels.to(dev, torch.float32).contiguous()
+        if self.multi_output != (f.output_len > 1):       # shapes the fused kernel does not cover: the reference's formulation
+            return self.evaluate_unfused(forest)
+        return torch.ops.evogp_cuda.tree_classification_accuracy(
+            f.pop_size, X.shape[0], f.max_tree_len, f.input_len, f.output_len, f.batch_node_value.contiguous(),
+            f.batch_node_type.contiguous(), f.batch_subtree_size.contiguous(), X, y, float(self.maximum))
+
+    def evaluate_unfused(self, forest: Forest):
+        """The reference's formulation on the fused batch_forward output (kept as the cross-check of `evaluate`)."""
         outputs = forest.batch_forward(self.datapoints)   # [P, N, O]
         if self.multi_output:
             # argmax(softmax(x)) with the reference's clipping (classification.py:62-64)

@@ -123,6 +123,17 @@ int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, u
                         const float *variables, float *results, void *workspace, size_t workspace_bytes,
                         void *stream);
 
+/* Fused form of Classification.evaluate (problem/classification.py:54-67), which the reference computes from
+ * batch_forward's [P, N, O] output with torch softmax / argmax: accuracy[i] = (1/N) * #{n : pred_i(n) == class_labels[n]}.
+ * outLen > 1: pred = arg-max over the outputs (first maximum; 0 when an output is NaN or the maximum infinite - torch's
+ * softmax makes every probability NaN there and argmax returns index 0).  outLen == 1: pred = clamp(round(out +
+ * max_class / 2), 0, max_class), round half to even.  class_labels: f32[dataPoints] class ids.  Nothing but one float
+ * per tree leaves the SM (BASELINE configs[3]: the batch_forward round trip would be 9.8 GB). */
+int evogp_classification_accuracy(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
+                                  const float *value, const int16_t *type, const int16_t *subtree_size,
+                                  const float *variables, const float *class_labels, float max_class, float *accuracy,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
 /* One whole generation step in one kernel ("next" row f-1; no counterpart in the reference's kernel.h — it fuses
  * what algorithm/genetic_programming.py:110-118, crossover/default.py and mutation/default.py do with ~14 torch
  * calls around three kernels):

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import gpu_util as G
-from conftest import make_data
+from conftest import ALL_FUNCS, make_data, make_forest
 
 pytestmark = pytest.mark.gpu
 
@@ -299,3 +299,47 @@ def test_generation_as_cuda_graph(api, orc):
     want = -orc.sr_fitness(*f_before, X.cpu().numpy(), y.cpu().numpy(), nthreads=8)
     ok = np.isfinite(want) & (np.abs(want) < 1e6)
     G.assert_close_fitness(fit[torch.from_numpy(ok)], want[ok], rtol=2e-3, what="graphed generation fitness")
+
+
+# --------------------------------------------------------------------------- fused classification accuracy
+def _reference_accuracy(outputs, labels, multi, maximum):
+    """problem/classification.py:54-67 verbatim, on [P, N, O] outputs."""
+    if multi:
+        prob = torch.clip(torch.softmax(outputs, dim=2), 1e-15, 1 - 1e-15)
+        pred = torch.argmax(prob, dim=2)
+    else:
+        pred = torch.clamp(torch.round(outputs + maximum / 2), 0, maximum).squeeze(-1)
+    return torch.sum(pred == labels, dim=1, dtype=torch.float32) / labels.shape[0]
+
+
+@pytest.mark.parametrize("O,N,L,funcs", [(3, 178, 64, ["+", "-", "*", "/"]), (3, 4096, 128, ["+", "-", "*", "/"]), (10, 300, 64, ALL_FUNCS),
+                                          (1, 150, 32, ["+", "-", "*", "/"]), (1, 1000, 64, ["+", "-", "*", "/", "sin"])])
+def test_classification_accuracy_is_fused(native, orc, O, N, L, funcs):
+    """accuracy computed inside the evaluation kernel == the reference's torch formulation applied to the CPU oracle's
+    batch_forward outputs (and to this library's own batch_forward), except where two outputs tie within rounding."""
+    native.load_ops()
+    from evogp_b200.problem import Classification
+    from evogp_b200.tree import Forest
+    P, V = 1500, 6
+    v, t, s = make_forest(orc, P, L, V, O, funcs, 4 if "if" in funcs else 5, keys=(61, 62), consts=(-1.0, 0.5, 2.0), out_prob=0.6)
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(N, V)).astype(np.float32)
+    classes = max(O, 3) if O > 1 else 3
+    labels = rng.integers(0, classes, N).astype(np.float32)
+    dv, dt, ds, dX, dl = G.to_dev(v, t, s, X, labels)
+    prob = Classification(datapoints=dX, labels=dl, multi_output=O > 1)
+    forest = Forest(V, O, dv, dt, ds)
+    got = prob.evaluate(forest)
+    own = prob.evaluate_unfused(forest)
+    torch.cuda.synchronize()
+    assert got.shape == (P,)
+    # same library, same per-node values: fused and unfused agree unless softmax rounding merges two distinct logits
+    diff_own = (got != own).float().mean().item()
+    assert diff_own <= 0.01, f"{diff_own:.3%} of trees differ from the unfused formulation"
+    assert (got - own).abs().max().item() <= 3.0 / N + 1e-7
+    # against the oracle's outputs (exact ops only are bit-comparable on the CPU; others within a few datapoints)
+    want = _reference_accuracy(torch.from_numpy(orc.batch_forward(v, t, s, X, O, nthreads=8)), torch.from_numpy(labels), O > 1, prob.maximum)
+    close = (got.cpu() - want).abs() <= (2.0 / N + 1e-7 if funcs is not ALL_FUNCS else 0.05)
+    assert close.float().mean().item() >= 0.98
+    # NaN / inf outputs predict class 0 (softmax turns the whole row NaN); a NaN single output matches nothing
+    assert torch.isfinite(got).all() and (got >= 0).all() and (got <= 1).all()
