@@ -39,6 +39,41 @@ struct Taus88 {
 };
 
 
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0, c1, 0, 0), key (k0, k1)
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Counter-based per-tree stream for evogp_generate's Philox mode (BASELINE.json north_star: "cuRAND/Philox per-thread
+// state"; the reference's RNG site is generate.cu:40-41): draw j of tree n is word j % 4 of
+// philox4x32_10(counter = (n, kPhiloxGenStream + j / 4), key = keys).  No state in memory, any tree reproducible alone.
+constexpr uint32_t kPhiloxGenStream = 0x10000u;
+struct PhiloxStream {
+    uint32_t n, k0, k1, blk, buf[4];
+    int have;
+    __device__ __forceinline__ PhiloxStream(uint32_t n_, uint32_t k0_, uint32_t k1_) : n(n_), k0(k0_), k1(k1_), blk(0), have(0) {}
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) {
+            philox4x32_10(n, kPhiloxGenStream + blk, k0, k1, buf);
+            ++blk;
+            have = 4;
+        }
+        const int i = 4 - have;
+        --have;
+        return i == 0 ? buf[0] : (i == 1 ? buf[1] : (i == 2 ? buf[2] : buf[3]));
+    }
+    __device__ __forceinline__ float uniform() { return __uint2float_rn(next()) * 2.3283064365386963e-10f; }
+};
+
 struct GrowParams {
     const float *leaf;     // [10]  depth -> leaf probability   (shared or global memory)
     const float *roul;     // [29]  cumulative function roulette
@@ -51,8 +86,8 @@ struct GrowParams {
 // The frame stack is a register: frames have strictly increasing depth, so "children still owed at depth d"
 // is a 4-bit field of one 64-bit word.  Subtree sizes need no stack: scanning the prefix backwards,
 // size[i] = 1 + size[c1] + size[c2] + ... with c1 = i + 1, c2 = c1 + size[c1].
-template <bool MULTI>
-__device__ inline int grow_tree(Taus88 &rng, const GrowParams &g, uint32_t *val, uint32_t *ts) {
+template <bool MULTI, class Rng = Taus88>
+__device__ inline int grow_tree(Rng &rng, const GrowParams &g, uint32_t *val, uint32_t *ts) {
     uint64_t owed = 1;   // root frame {1, 0}
     int d = 0, cnt = 0;
     while (d >= 0 && cnt < (int)g.L) {

@@ -32,7 +32,7 @@ struct GenArgs {
     int trees_per_block, pitch;
 };
 
-template <bool MULTI>
+template <bool MULTI, bool PHILOX>
 __global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
     extern __shared__ uint32_t gsm[];
     __shared__ float s_leaf[kMaxFullDepth];
@@ -50,11 +50,17 @@ __global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
     if ((int)threadIdx.x < T && n < g.P) {
         uint32_t *val = s_val + (size_t)threadIdx.x * pitch;
         uint32_t *ts = s_ts + (size_t)threadIdx.x * pitch;
-        Taus88 rng(tree_seed(n, g.keys[0], g.keys[1]));
         GrowParams gp;
         gp.leaf = s_leaf; gp.roul = s_roul; gp.consts = g.consts;
         gp.L = g.L; gp.V = g.V; gp.O = g.O; gp.S = g.S; gp.outProb = g.outProb; gp.constProb = g.constProb;
-        const int cnt = grow_tree<MULTI>(rng, gp, val, ts);
+        int cnt;
+        if constexpr (PHILOX) {
+            PhiloxStream rng(n, g.keys[0], g.keys[1]);
+            cnt = grow_tree<MULTI>(rng, gp, val, ts);
+        } else {
+            Taus88 rng(tree_seed(n, g.keys[0], g.keys[1]));
+            cnt = grow_tree<MULTI>(rng, gp, val, ts);
+        }
         len = cnt > 0 ? (int)(ts[0] >> 16) : 0;
         if (cnt < pitch) ts[cnt] = 0;
         // remember the valid length in the padding word of the row (pitch > L always)
@@ -97,10 +103,10 @@ __global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
 
 using namespace evogp;
 
-extern "C" int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
-                              unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
-                              const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
-                              float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream) {
+static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
+                         unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
+                         const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
+                         float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream) {
     // torch_wrapper.cu:48-54
     EVOGP_REQUIRE(popSize > 0, "pop_size must be larger than 0, got %u", popSize);
     EVOGP_REQUIRE(maxGPLen > 0 && maxGPLen <= (unsigned)kMaxStack, "gp_len must be in (0, %d], got %u", kMaxStack, maxGPLen);
@@ -126,13 +132,30 @@ extern "C" int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varL
     const size_t smem = per_tree * T;
     const unsigned grid = (popSize + T - 1) / T;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (outLen > 1) {
-        EVOGP_CUDA(cudaFuncSetAttribute(generate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        generate_kernel<true><<<grid, threads, smem, st>>>(a);
-    } else {
-        EVOGP_CUDA(cudaFuncSetAttribute(generate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        generate_kernel<false><<<grid, threads, smem, st>>>(a);
-    }
+    auto launch = [&](auto kern) -> int {
+        EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(a);
+        return EVOGP_OK;
+    };
+    if (outLen > 1) rc = philox ? launch(generate_kernel<true, true>) : launch(generate_kernel<true, false>);
+    else rc = philox ? launch(generate_kernel<false, true>) : launch(generate_kernel<false, false>);
+    if (rc) return rc;
     count_launch();
     return check_launch("generate");
+}
+
+extern "C" int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
+                              unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
+                              const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
+                              float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream) {
+    return generate_impl(false, popSize, maxGPLen, varLen, outLen, constSamplesLen, outProb, constProb, keys, depth2leafProbs,
+                         rouletteFuncs, constSamples, value_res, type_res, subtree_size_res, stream);
+}
+
+extern "C" int evogp_generate_philox(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
+                                     unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
+                                     const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
+                                     float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream) {
+    return generate_impl(true, popSize, maxGPLen, varLen, outLen, constSamplesLen, outProb, constProb, keys, depth2leafProbs,
+                         rouletteFuncs, constSamples, value_res, type_res, subtree_size_res, stream);
 }

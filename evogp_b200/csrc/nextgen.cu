@@ -20,18 +20,11 @@
 
 namespace evogp {
 
-// Philox4x32-10 (Salmon et al., SC'11), counter = (n, stream, 0, 0), key = (k0, k1)
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-    uint32_t c2 = 0, c3 = 0;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
+// draws of child n: Philox4x32-10 blocks (n, 0) and (n, 1) under the generation's keys (gen_tree.cuh)
+__device__ __forceinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t o[4];
+    philox4x32_10(c0, c1, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 struct NextGenArgs {
@@ -92,7 +85,7 @@ __global__ void __launch_bounds__(256) nextgen_kernel(NextGenArgs g) {
             continue;
         }
         // ---- draws (warp-uniform: every lane computes the same Philox block) ----
-        const uint4 r0 = philox4x32_10((uint32_t)n, 0u, k0, k1), r1 = philox4x32_10((uint32_t)n, 1u, k0, k1);
+        const uint4 r0 = philox_block((uint32_t)n, 0u, k0, k1), r1 = philox_block((uint32_t)n, 1u, k0, k1);
         const size_t lrow = (size_t)g.order[r0.x % (uint32_t)g.survivors] * L;
         const size_t rrow = (size_t)g.order[r0.y % (uint32_t)g.survivors] * L;
         const int llen = g.size[lrow], rlen = g.size[rrow];

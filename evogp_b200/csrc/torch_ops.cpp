@@ -43,7 +43,7 @@ Tensor eval_workspace(int64_t pop, int64_t len, const Tensor &like, size_t &byte
     return at::empty({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte).device(like.device()));
 }
 
-Tensor3 tree_generate(int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t out_len, int64_t const_samples_len,
+Tensor3 generate_impl(bool philox, int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t out_len, int64_t const_samples_len,
                       double out_prob, double const_prob, Tensor keys, Tensor depth2leaf_probs, Tensor roulette_funcs,
                       Tensor const_samples) {
     TORCH_CHECK(pop_size > 0, "pop_size must larger than 0, but got ", pop_size);
@@ -59,14 +59,59 @@ Tensor3 tree_generate(int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t
     check_tensor(const_samples, {const_samples_len}, at::kFloat, "const_samples");
     c10::cuda::CUDAGuard guard(keys.device());
     auto out = alloc_forest(pop_size, gp_len, keys);
-    check_rc(evogp_generate((unsigned)pop_size, (unsigned)gp_len, (unsigned)var_len, (unsigned)out_len,
-                            (unsigned)const_samples_len, (float)out_prob, (float)const_prob,
-                            static_cast<const unsigned *>(keys.data_ptr()), depth2leaf_probs.data_ptr<float>(),
-                            roulette_funcs.data_ptr<float>(), const_samples.data_ptr<float>(),
-                            std::get<0>(out).data_ptr<float>(), std::get<1>(out).data_ptr<int16_t>(),
-                            std::get<2>(out).data_ptr<int16_t>(), cur_stream(keys)),
-             "tree_generate");
+    auto fn = philox ? &evogp_generate_philox : &evogp_generate;
+    check_rc(fn((unsigned)pop_size, (unsigned)gp_len, (unsigned)var_len, (unsigned)out_len, (unsigned)const_samples_len,
+                (float)out_prob, (float)const_prob, static_cast<const unsigned *>(keys.data_ptr()),
+                depth2leaf_probs.data_ptr<float>(), roulette_funcs.data_ptr<float>(), const_samples.data_ptr<float>(),
+                std::get<0>(out).data_ptr<float>(), std::get<1>(out).data_ptr<int16_t>(), std::get<2>(out).data_ptr<int16_t>(),
+                cur_stream(keys)),
+             philox ? "tree_generate_philox" : "tree_generate");
     return out;
+}
+
+Tensor3 tree_generate(int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t out_len, int64_t const_samples_len,
+                      double out_prob, double const_prob, Tensor keys, Tensor depth2leaf_probs, Tensor roulette_funcs,
+                      Tensor const_samples) {
+    return generate_impl(false, pop_size, gp_len, var_len, out_len, const_samples_len, out_prob, const_prob, keys, depth2leaf_probs,
+                         roulette_funcs, const_samples);
+}
+
+Tensor3 tree_generate_philox(int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t out_len, int64_t const_samples_len,
+                             double out_prob, double const_prob, Tensor keys, Tensor depth2leaf_probs, Tensor roulette_funcs,
+                             Tensor const_samples) {
+    return generate_impl(true, pop_size, gp_len, var_len, out_len, const_samples_len, out_prob, const_prob, keys, depth2leaf_probs,
+                         roulette_funcs, const_samples);
+}
+
+Tensor3 tree_extract_subtree(int64_t pop_size, int64_t gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor positions) {
+    TORCH_CHECK(pop_size > 0, "pop_size must larger than 0, but got ", pop_size);
+    TORCH_CHECK(0 < gp_len && gp_len <= EVOGP_MAX_STACK, "gp_len must be in range (0, ", EVOGP_MAX_STACK, "], but got ", gp_len);
+    check_tensor(value, {pop_size, gp_len}, at::kFloat, "value");
+    check_tensor(node_type, {pop_size, gp_len}, at::kShort, "node_type");
+    check_tensor(subtree_size, {pop_size, gp_len}, at::kShort, "subtree_size");
+    check_tensor(positions, {pop_size}, at::kInt, "positions");
+    c10::cuda::CUDAGuard guard(value.device());
+    auto out = alloc_forest(pop_size, gp_len, value);
+    check_rc(evogp_extract_subtree((int)pop_size, (int)gp_len, value.data_ptr<float>(), node_type.data_ptr<int16_t>(),
+                                   subtree_size.data_ptr<int16_t>(), positions.data_ptr<int>(), std::get<0>(out).data_ptr<float>(),
+                                   std::get<1>(out).data_ptr<int16_t>(), std::get<2>(out).data_ptr<int16_t>(), cur_stream(value)),
+             "tree_extract_subtree");
+    return out;
+}
+
+Tensor tree_tournament_select(Tensor fitness, int64_t tournament_size, double best_probability, bool replace, int64_t winner_cnt,
+                              Tensor keys) {
+    TORCH_CHECK(fitness.is_cuda() && fitness.is_contiguous() && fitness.dim() == 1 && fitness.scalar_type() == at::kFloat,
+                "fitness must be a contiguous 1-D float CUDA tensor");
+    check_tensor(keys, {2}, at::kUInt32, "keys");
+    TORCH_CHECK(winner_cnt > 0, "winner_cnt must larger than 0, but got ", winner_cnt);
+    c10::cuda::CUDAGuard guard(fitness.device());
+    auto winners = at::empty({winner_cnt}, fitness.options().dtype(at::kInt));
+    check_rc(evogp_tournament_select((int)fitness.numel(), fitness.data_ptr<float>(), (int)tournament_size, (float)best_probability,
+                                     replace ? 1 : 0, (int)winner_cnt, static_cast<const unsigned *>(keys.data_ptr()),
+                                     winners.data_ptr<int>(), cur_stream(fitness)),
+             "tree_tournament_select");
+    return winners;
 }
 
 Tensor3 tree_mutate(int64_t pop_size, int64_t gp_len, Tensor value_ori, Tensor type_ori, Tensor subtree_size_ori,
@@ -236,6 +281,9 @@ TORCH_LIBRARY(evogp_cuda, m) {
     m.def("tree_evaluate(int pop_size, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
     m.def("tree_SR_fitness(int pop_size, int data_points, int gp_len, int var_len, int out_len, bool useMSE, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor labels, int kernel_type) -> Tensor");
     m.def("tree_next_generation(int pop_size, int gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor order, int elite_cnt, int survivor_cnt, float mutation_rate, int var_len, int out_len, float out_prob, float const_prob, Tensor depth2leaf_probs, Tensor roulette_funcs, Tensor const_samples, Tensor keys) -> (Tensor, Tensor, Tensor)");
+    m.def("tree_generate_philox(int pop_size, int gp_len, int var_len, int out_len, int const_samples_len, float out_prob, float const_prob, Tensor keys, Tensor depth2leaf_probs, Tensor roulette_funcs, Tensor const_samples) -> (Tensor, Tensor, Tensor)");
+    m.def("tree_extract_subtree(int pop_size, int gp_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor positions) -> (Tensor, Tensor, Tensor)");
+    m.def("tree_tournament_select(Tensor fitness, int tournament_size, float best_probability, bool replace, int winner_cnt, Tensor keys) -> Tensor");
     m.def("tree_classification_accuracy(int pop_size, int data_points, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables, Tensor class_labels, float max_class) -> Tensor");
     m.def("tree_batch_forward(int pop_size, int data_points, int gp_len, int var_len, int out_len, Tensor value, Tensor node_type, Tensor subtree_size, Tensor variables) -> Tensor");
 }
@@ -248,5 +296,8 @@ TORCH_LIBRARY_IMPL(evogp_cuda, CUDA, m) {
     m.impl("tree_SR_fitness", &tree_SR_fitness);
     m.impl("tree_batch_forward", &tree_batch_forward);
     m.impl("tree_classification_accuracy", &tree_classification_accuracy);
+    m.impl("tree_generate_philox", &tree_generate_philox);
+    m.impl("tree_extract_subtree", &tree_extract_subtree);
+    m.impl("tree_tournament_select", &tree_tournament_select);
     m.impl("tree_next_generation", &tree_next_generation);
 }

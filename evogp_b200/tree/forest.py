@@ -54,9 +54,13 @@ class Forest:
         return Forest.generate_with_keys(pop_size, descriptor, keys)
 
     @staticmethod
-    def generate_with_keys(pop_size: int, descriptor: GenerateDescriptor, keys: Tensor) -> "Forest":
+    def generate_with_keys(pop_size: int, descriptor: GenerateDescriptor, keys: Tensor, rng: str = "taus88") -> "Forest":
+        """rng="taus88": the reference's per-tree generator, bit-identical trees (generate.cu:40-41);
+        rng="philox": counter-based Philox4x32-10 draws (`tree_generate_philox`) - same growth rules, other trees."""
+        assert rng in ("taus88", "philox"), f"rng should be 'taus88' or 'philox', but got {rng}"
         d = descriptor
-        v, t, s = _ops.tree_generate(pop_size, d.max_tree_len, d.input_len, d.output_len, d.const_samples.shape[0],
+        op = _ops.tree_generate if rng == "taus88" else _ops.tree_generate_philox
+        v, t, s = op(pop_size, d.max_tree_len, d.input_len, d.output_len, d.const_samples.shape[0],
                                      d.out_prob, d.const_prob, keys, d.depth2leaf_probs, d.roulette_funcs,
                                      d.const_samples)
         return Forest(d.input_len, d.output_len, v, t, s)

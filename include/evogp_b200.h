@@ -60,6 +60,15 @@ int evogp_generate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigne
                    const float *rouletteFuncs, const float *constSamples, float *value_res, int16_t *type_res,
                    int16_t *subtree_size_res, void *stream);
 
+/* Philox mode of evogp_generate (BASELINE.json north_star: "cuRAND/Philox per-thread state"; the reference's generator
+ * site is generate.cu:40-41).  Same growth rules and draw order; draw j of tree n is word j % 4 of
+ * Philox4x32-10(counter = (n, 0x10000 + j / 4), key = keys): counter-based, nothing to seed or store.  Trees differ
+ * from the taus88 mode (which stays the bit-exact-with-the-reference default); parity: oracle_generate_philox. */
+int evogp_generate_philox(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, unsigned constSamplesLen,
+                          float outProb, float constProb, const unsigned *keys, const float *depth2leafProbs,
+                          const float *rouletteFuncs, const float *constSamples, float *value_res, int16_t *type_res,
+                          int16_t *subtree_size_res, void *stream);
+
 /* replaces mutate(), kernel.h:40-53 (mutation.cu:186-219). */
 int evogp_mutate(int popSize, int gpLen, const float *value_ori, const int16_t *type_ori,
                  const int16_t *subtree_size_ori, const int *mutateIndices, const float *value_new,
@@ -122,6 +131,21 @@ int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, u
                         const float *value, const int16_t *type, const int16_t *subtree_size,
                         const float *variables, float *results, void *workspace, size_t workspace_bytes,
                         void *stream);
+
+/* Native form of vmap_subtree (src/evogp/algorithm/mutation/mutation_utils.py:6-48), the gather the reference's Hoist /
+ * Insert / Delete mutations build from torch ops: row n of the result = the subtree of tree n rooted at positions[n]
+ * (int32[popSize]), moved to the front, tail zero-filled; a position outside [0, gpLen) gives an all-zero row. */
+int evogp_extract_subtree(int popSize, int gpLen, const float *value, const int16_t *type, const int16_t *subtree_size,
+                          const int *positions, float *value_res, int16_t *type_res, int16_t *subtree_size_res, void *stream);
+
+/* Native form of TournamentSelection (src/evogp/algorithm/selection/tournament.py:59-133; the reference draws contenders
+ * with torch.multinomial over a [k_times, P] matrix under vmap, :73-79): winners[j], j < winnerCnt, is the nth best of
+ * tournamentSize contenders, nth geometric in bestProbability (:97-101; 1 = always the best), NaN fitness ranking last.
+ * replace != 0: contenders are independent uniform draws; else tournaments are consecutive slices of a pseudo-random
+ * permutation of the population, a fresh one every popSize / tournamentSize tournaments.  Draws: Philox4x32-10 keyed by
+ * keys[2] (counter-based: deterministic in keys, not torch's stream).  winners: int32[winnerCnt] row indices. */
+int evogp_tournament_select(int popSize, const float *fitness, int tournamentSize, float bestProbability, int replace,
+                            int winnerCnt, const unsigned *keys, int *winners, void *stream);
 
 /* Fused form of Classification.evaluate (problem/classification.py:54-67), which the reference computes from
  * batch_forward's [P, N, O] output with torch softmax / argmax: accuracy[i] = (1/N) * #{n : pred_i(n) == class_labels[n]}.

@@ -18,6 +18,12 @@ from .oracle import (  # noqa: F401
     batch_forward,
     sr_fitness,
     generate,
+    generate_philox,
+    philox,
+    extract_subtree,
+    tournament,
+    feistel_perm,
+    next_generation,
     crossover,
     mutate,
     hash32,

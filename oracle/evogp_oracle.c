@@ -348,6 +348,45 @@ uint32_t oracle_taus88_nth(uint32_t seed, int n) {
     return v;
 }
 
+/* Philox4x32-10 (Salmon et al., SC'11), counter (c0, c1, 0, 0), key (k0, k1) - the counter-based generator of this
+ * library's own additions (evogp_b200/csrc/gen_tree.cuh): evogp_generate_philox, evogp_next_generation,
+ * evogp_tournament_select.  Restated here so that those kernels have bit-exact parity tests. */
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    uint32_t c2 = 0, c3 = 0;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+void oracle_philox(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t *out) { philox4x32_10(c0, c1, k0, k1, out); }
+
+/* the per-tree random stream: thrust taus88 (the reference's), or Philox blocks (n, 0x10000 + j / 4) word j % 4 */
+#define ORC_PHILOX_GEN_STREAM 0x10000u
+typedef struct {
+    int philox;
+    taus88_t t;
+    uint32_t n, k0, k1, blk, buf[4];
+    int have;
+} rng_t;
+static void rng_seed_taus(rng_t *g, uint32_t seed) { g->philox = 0; taus88_seed(&g->t, seed); }
+static void rng_seed_philox(rng_t *g, uint32_t n, uint32_t k0, uint32_t k1) {
+    g->philox = 1; g->n = n; g->k0 = k0; g->k1 = k1; g->blk = 0; g->have = 0;
+}
+static uint32_t rng_next(rng_t *g) {
+    if (!g->philox) return taus88_next(&g->t);
+    if (g->have == 0) {
+        philox4x32_10(g->n, ORC_PHILOX_GEN_STREAM + g->blk, g->k0, g->k1, g->buf);
+        g->blk++;
+        g->have = 4;
+    }
+    return g->buf[4 - g->have--];
+}
+static float rng_uniform(rng_t *g) { return (float)rng_next(g) / 4294967296.0f; }
+
 /*
  * generate.cu:16-173 (treeGPGenerate).  Draw order per node:
  *   u (leaf test vs depth2leaf[depth])                        :71
@@ -360,88 +399,96 @@ uint32_t oracle_taus88_nth(uint32_t seed, int n) {
  * is defined by the reference — this restatement zero-fills the tail.
  * Deviation (documented): depth >= MAX_FULL_DEPTH reads leafProbs out of
  * bounds in the reference; here it is treated as probability 1 (leaf).
+ * Returns the node count; gv / gt / gs receive the tree (ORC_MAX_STACK entries each).
  */
-void oracle_generate(unsigned P, unsigned L, unsigned V, unsigned O, unsigned S, float outProb, float constProb,
-                     const uint32_t *keys, const float *depth2leaf, const float *roulette, const float *constSamples,
-                     float *value_res, int16_t *type_res, int16_t *size_res, int nthreads) {
+static int grow_one(rng_t *g, int cap, unsigned V, unsigned O, unsigned S, float outProb, float constProb,
+                    const float *depth2leaf, const float *roulette, const float *constSamples, float *gv, int16_t *gt,
+                    int16_t *gs) {
     const int multi = O > 1;
+    int16_t fr_childs[ORC_MAX_STACK], fr_depth[ORC_MAX_STACK];
+    int nodeSize[ORC_MAX_STACK];
+    fr_childs[0] = 1;
+    fr_depth[0] = 0;
+    int topGP = 0, top = 1;
+    while (top > 0 && topGP < cap) {
+        --top;
+        int16_t cd_childs = (int16_t)(fr_childs[top] - 1), cd_depth = fr_depth[top];
+        int16_t new_childs = 0, new_depth = 0;
+        float nv;
+        int16_t nt;
+        float leafp = cd_depth < ORC_MAX_FULL_DEPTH ? depth2leaf[cd_depth] : 2.0f;
+        if (rng_uniform(g) >= leafp) {
+            float r = rng_uniform(g);
+            int k = 0;
+            for (int i = F_END - 1; i >= 0; i--)
+                if (r >= roulette[i]) {
+                    k = i + 1;
+                    break;
+                }
+            int16_t t = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
+            nv = (float)k;
+            nt = t;
+            if (multi && rng_uniform(g) <= outProb) {
+                uint32_t bits = ((uint32_t)(uint16_t)(int16_t)k) | ((uint32_t)(uint16_t)(int16_t)(rng_next(g) % O) << 16);
+                memcpy(&nv, &bits, 4);
+                nt = (int16_t)(t + NT_OUT);
+            }
+            new_childs = (int16_t)(t - 1);
+            new_depth = (int16_t)(cd_depth + 1);
+        } else {
+            if (rng_uniform(g) <= constProb) {
+                nv = constSamples[rng_next(g) % S];
+                nt = NT_CONST;
+            } else {
+                nv = (float)(rng_next(g) % V);
+                nt = NT_VAR;
+            }
+        }
+        gv[topGP] = nv;
+        gt[topGP] = nt;
+        topGP++;
+        if (cd_childs > 0) {
+            fr_childs[top] = cd_childs;
+            fr_depth[top] = cd_depth;
+            top++;
+        }
+        if (new_childs > 0) {
+            fr_childs[top] = new_childs;
+            fr_depth[top] = new_depth;
+            top++;
+        }
+    }
+    top = 0;
+    for (int i = topGP - 1; i >= 0; i--) {
+        int t = gt[i] & NT_MASK;
+        int sz = 1;
+        if (t == NT_UFUNC) {
+            sz += nodeSize[--top];
+        } else if (t == NT_BFUNC) {
+            sz += nodeSize[--top];
+            sz += nodeSize[--top];
+        } else if (t >= NT_TFUNC) {
+            sz += nodeSize[--top];
+            sz += nodeSize[--top];
+            sz += nodeSize[--top];
+        }
+        nodeSize[top++] = sz;
+        gs[i] = (int16_t)sz;
+    }
+    return topGP;
+}
+
+static void generate_any(int philox, unsigned P, unsigned L, unsigned V, unsigned O, unsigned S, float outProb, float constProb,
+                         const uint32_t *keys, const float *depth2leaf, const float *roulette, const float *constSamples,
+                         float *value_res, int16_t *type_res, int16_t *size_res, int nthreads) {
 #pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 0 ? nthreads : 1)
     for (long n = 0; n < (long)P; n++) {
         float gv[ORC_MAX_STACK];
         int16_t gt[ORC_MAX_STACK], gs[ORC_MAX_STACK];
-        int16_t fr_childs[ORC_MAX_STACK], fr_depth[ORC_MAX_STACK];
-        int nodeSize[ORC_MAX_STACK];
-        taus88_t g;
-        taus88_seed(&g, oracle_hash((uint32_t)n, keys[0], keys[1]));
-        fr_childs[0] = 1;
-        fr_depth[0] = 0;
-        int topGP = 0, top = 1;
-        while (top > 0 && topGP < ORC_MAX_STACK) {
-            --top;
-            int16_t cd_childs = (int16_t)(fr_childs[top] - 1), cd_depth = fr_depth[top];
-            int16_t new_childs = 0, new_depth = 0;
-            float nv;
-            int16_t nt;
-            float leafp = cd_depth < ORC_MAX_FULL_DEPTH ? depth2leaf[cd_depth] : 2.0f;
-            if (taus88_uniform(&g) >= leafp) {
-                float r = taus88_uniform(&g);
-                int k = 0;
-                for (int i = F_END - 1; i >= 0; i--)
-                    if (r >= roulette[i]) {
-                        k = i + 1;
-                        break;
-                    }
-                int16_t t = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
-                nv = (float)k;
-                nt = t;
-                if (multi && taus88_uniform(&g) <= outProb) {
-                    uint32_t bits = ((uint32_t)(uint16_t)(int16_t)k) |
-                                    ((uint32_t)(uint16_t)(int16_t)(taus88_next(&g) % O) << 16);
-                    memcpy(&nv, &bits, 4);
-                    nt = (int16_t)(t + NT_OUT);
-                }
-                new_childs = (int16_t)(t - 1);
-                new_depth = (int16_t)(cd_depth + 1);
-            } else {
-                if (taus88_uniform(&g) <= constProb) {
-                    nv = constSamples[taus88_next(&g) % S];
-                    nt = NT_CONST;
-                } else {
-                    nv = (float)(taus88_next(&g) % V);
-                    nt = NT_VAR;
-                }
-            }
-            gv[topGP] = nv;
-            gt[topGP] = nt;
-            topGP++;
-            if (cd_childs > 0) {
-                fr_childs[top] = cd_childs;
-                fr_depth[top] = cd_depth;
-                top++;
-            }
-            if (new_childs > 0) {
-                fr_childs[top] = new_childs;
-                fr_depth[top] = new_depth;
-                top++;
-            }
-        }
-        top = 0;
-        for (int i = topGP - 1; i >= 0; i--) {
-            int t = gt[i] & NT_MASK;
-            int sz = 1;
-            if (t == NT_UFUNC) {
-                sz += nodeSize[--top];
-            } else if (t == NT_BFUNC) {
-                sz += nodeSize[--top];
-                sz += nodeSize[--top];
-            } else if (t >= NT_TFUNC) {
-                sz += nodeSize[--top];
-                sz += nodeSize[--top];
-                sz += nodeSize[--top];
-            }
-            nodeSize[top++] = sz;
-            gs[i] = (int16_t)sz;
-        }
+        rng_t g;
+        if (philox) rng_seed_philox(&g, (uint32_t)n, keys[0], keys[1]);
+        else rng_seed_taus(&g, oracle_hash((uint32_t)n, keys[0], keys[1]));
+        grow_one(&g, ORC_MAX_STACK, V, O, S, outProb, constProb, depth2leaf, roulette, constSamples, gv, gt, gs);
         int len = gs[0];
         float *ov = value_res + (size_t)n * L;
         int16_t *ot = type_res + (size_t)n * L;
@@ -453,6 +500,19 @@ void oracle_generate(unsigned P, unsigned L, unsigned V, unsigned O, unsigned S,
             os[i] = in ? gs[i] : 0;
         }
     }
+}
+
+void oracle_generate(unsigned P, unsigned L, unsigned V, unsigned O, unsigned S, float outProb, float constProb,
+                     const uint32_t *keys, const float *depth2leaf, const float *roulette, const float *constSamples,
+                     float *value_res, int16_t *type_res, int16_t *size_res, int nthreads) {
+    generate_any(0, P, L, V, O, S, outProb, constProb, keys, depth2leaf, roulette, constSamples, value_res, type_res, size_res, nthreads);
+}
+
+/* evogp_generate_philox (evogp_b200/csrc/generate.cu): the same growth, draws from the Philox stream above */
+void oracle_generate_philox(unsigned P, unsigned L, unsigned V, unsigned O, unsigned S, float outProb, float constProb,
+                            const uint32_t *keys, const float *depth2leaf, const float *roulette, const float *constSamples,
+                            float *value_res, int16_t *type_res, int16_t *size_res, int nthreads) {
+    generate_any(1, P, L, V, O, S, outProb, constProb, keys, depth2leaf, roulette, constSamples, value_res, type_res, size_res, nthreads);
 }
 
 /* ------------------------------------------------------------------ */
@@ -563,6 +623,168 @@ void oracle_mutate(int P, int L, const float *value, const int16_t *type, const 
         }
         tree_replace(L, pos, 0, nsub, pos + osub, old_size, diff, lv, lt, ls, nvalue + o, ntype + o, nsize + o, ov + o,
                      ot + o, os + o);
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* This library's own operators (no counterpart in the reference's      */
+/* kernel.h): restated so that their kernels have bit-exact parity.     */
+/* ------------------------------------------------------------------ */
+
+/* evogp_extract_subtree (csrc/select.cu) = vmap_subtree / subtensor of
+ * src/evogp/algorithm/mutation/mutation_utils.py:6-48: row n becomes the subtree rooted at pos[n], tail zero. */
+void oracle_extract_subtree(int P, int L, const float *value, const int16_t *type, const int16_t *size, const int *pos,
+                            float *ov, int16_t *ot, int16_t *os) {
+    for (long n = 0; n < (long)P; n++) {
+        size_t o = (size_t)n * L;
+        int p = pos[n];
+        int ok = p >= 0 && p < L;
+        int len = ok ? size[o + p] : 0;
+        for (int j = 0; j < L; j++) {
+            int in = ok && j < len && p + j < L;
+            ov[o + j] = in ? value[o + p + j] : 0.0f;
+            ot[o + j] = in ? type[o + p + j] : 0;
+            os[o + j] = in ? size[o + p + j] : 0;
+        }
+    }
+}
+
+/* keyed bijection of [0, n): 4-round Feistel network on 2 * half_bits bits, cycle-walked (csrc/select.cu) */
+static uint32_t feistel_perm(uint32_t x, uint32_t n, int half_bits, const uint32_t rk[4]) {
+    const uint32_t mask = (1u << half_bits) - 1u;
+    do {
+        uint32_t l = x >> half_bits, r = x & mask;
+        for (int i = 0; i < 4; i++) {
+            uint32_t f = (r ^ rk[i]) * 0x9E3779B1u;
+            f ^= f >> 15;
+            f *= 0x85EBCA77u;
+            f ^= f >> 13;
+            uint32_t nl = r;
+            r = (l ^ f) & mask;
+            l = nl;
+        }
+        x = (l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+void oracle_feistel_perm(uint32_t n, uint32_t round, const uint32_t *keys, uint32_t *out) {
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < (unsigned long long)n) half_bits++;
+    uint32_t rk[4];
+    philox4x32_10(round, 0x30000u, keys[0], keys[1], rk);
+    for (uint32_t x = 0; x < n; x++) out[x] = feistel_perm(x, n, half_bits, rk);
+}
+
+/* evogp_tournament_select (csrc/select.cu): the semantics of TournamentSelection
+ * (src/evogp/algorithm/selection/tournament.py:59-133) with counter-based draws.  Tournament j: contenders i = 0..T-1
+ * are Philox words (with replacement) or slice j % (P / T) of permutation j / (P / T) (without); the winner is the nth
+ * best, nth geometric in best_p (tournament.py:97-101), ties broken by draw order. */
+void oracle_tournament(int P, const float *fitness, int T, float best_p, int replace, int count, const uint32_t *keys,
+                       int *winners) {
+    const uint32_t k0 = keys[0], k1 = keys[1];
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < (unsigned long long)P) half_bits++;
+    const int per_round = P / T;
+    uint32_t *cs = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)T);
+    float *fs = (float *)malloc(sizeof(float) * (size_t)T);
+    for (int j = 0; j < count; j++) {
+        uint32_t d[4];
+        philox4x32_10((uint32_t)j, 0x20000u, k0, k1, d);
+        int nth = 0;
+        if (best_p < 1.0f) {
+            float u = (float)d[0] / 4294967296.0f, q = 1.0f - best_p, thr = q;
+            while (nth < T && u <= thr) {
+                nth++;
+                thr = thr * q;
+            }
+            if (nth >= T) nth = 0;
+        }
+        int round = j / per_round, slot = j - round * per_round;
+        uint32_t rk[4];
+        philox4x32_10((uint32_t)round, 0x30000u, k0, k1, rk);
+        for (int i = 0; i < T; i++) {
+            if (replace) {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)j, 0x20000u + 1u + (uint32_t)(i >> 2), k0, k1, w);
+                cs[i] = w[i & 3] % (uint32_t)P;
+            } else {
+                cs[i] = feistel_perm((uint32_t)(slot * T + i), (uint32_t)P, half_bits, rk);
+            }
+            float f = fitness[cs[i]];
+            fs[i] = f == f ? f : -INFINITY;
+        }
+        int win = 0;
+        for (int i = 0; i < T; i++) {
+            int better = 0;
+            for (int m = 0; m < T; m++)
+                if (m != i && (fs[m] > fs[i] || (fs[m] == fs[i] && m < i))) better++;
+            if (better == nth) win = (int)cs[i];
+        }
+        winners[j] = win;
+    }
+    free(cs);
+    free(fs);
+}
+
+/* evogp_next_generation (csrc/nextgen.cu): a whole generation step — elitism, DefaultCrossover among the survivors,
+ * DefaultMutation with freshly grown donors (reference: algorithm/genetic_programming.py:110-118,
+ * crossover/default.py, mutation/default.py; splice rules mutation.cu:5-115 incl. the fallbacks :150,163,256,279) —
+ * with the kernel's counter-based draws:  r0 = philox(n, 0), r1 = philox(n, 1) under the generation's keys;
+ *   left parent  = order[r0.x % survivors], right parent = order[r0.y % survivors],
+ *   left pos     = r0.z % len(left),        right pos    = r0.w % len(right),
+ *   mutate iff float(r1.x) * 2^-32 < rate,  mutation pos = r1.y % len(child),
+ *   donor        = grow (taus88 seeded with hash(n, k0 ^ 0x5bd1e995, k1)), rows capped at L nodes.
+ * Built from tree_replace() above (the reference's root->pos walk), not from the kernel's closed form. */
+void oracle_next_generation(int P, int L, const float *value, const int16_t *type, const int16_t *size,
+                            const long long *order, int elite, int survivors, float rate, unsigned V, unsigned O, unsigned S,
+                            float outProb, float constProb, const float *depth2leaf, const float *roulette,
+                            const float *constSamples, const uint32_t *keys, float *ov, int16_t *ot, int16_t *os,
+                            int nthreads) {
+    const uint32_t k0 = keys[0], k1 = keys[1];
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 0 ? nthreads : 1)
+    for (long n = 0; n < (long)P; n++) {
+        size_t oo = (size_t)n * L;
+        if (n < elite) {
+            size_t src = (size_t)order[n] * L;
+            memcpy(ov + oo, value + src, sizeof(float) * (size_t)L);
+            memcpy(ot + oo, type + src, sizeof(int16_t) * (size_t)L);
+            memcpy(os + oo, size + src, sizeof(int16_t) * (size_t)L);
+            continue;
+        }
+        uint32_t r0[4], r1[4];
+        philox4x32_10((uint32_t)n, 0u, k0, k1, r0);
+        philox4x32_10((uint32_t)n, 1u, k0, k1, r1);
+        size_t lrow = (size_t)order[r0[0] % (uint32_t)survivors] * L, rrow = (size_t)order[r0[1] % (uint32_t)survivors] * L;
+        int llen = size[lrow], rlen = size[rrow];
+        int lpos = (int)(r0[2] % (uint32_t)(llen > 1 ? llen : 1)), rpos = (int)(r0[3] % (uint32_t)(rlen > 1 ? rlen : 1));
+        int rows_ok = llen >= 1 && llen <= L && rlen >= 1 && rlen <= L;
+        /* crossover into a temporary child */
+        float cv[ORC_MAX_STACK];
+        int16_t ct[ORC_MAX_STACK], cs[ORC_MAX_STACK];
+        int lsub = rows_ok ? size[lrow + lpos] : 0, rsub = rows_ok ? size[rrow + rpos] : 0;
+        if (rows_ok && rsub >= 1 && llen + rsub - lsub <= L)
+            tree_replace((unsigned)L, lpos, rpos, rsub, lpos + lsub, llen, rsub - lsub, value + lrow, type + lrow, size + lrow,
+                         value + rrow, type + rrow, size + rrow, cv, ct, cs);
+        else
+            copy_row((unsigned)L, llen >= 0 && llen <= L ? llen : 0, value + lrow, type + lrow, size + lrow, cv, ct, cs);
+        int clen = cs[0];
+        float u = (float)r1[0] / 4294967296.0f;
+        if (u < rate) {
+            float dv[ORC_MAX_STACK];
+            int16_t dt[ORC_MAX_STACK], ds[ORC_MAX_STACK];
+            rng_t g;
+            rng_seed_taus(&g, oracle_hash((uint32_t)n, k0 ^ 0x5bd1e995u, k1));
+            int cnt = grow_one(&g, L, V, O, S, outProb, constProb, depth2leaf, roulette, constSamples, dv, dt, ds);
+            int dlen = cnt > 0 ? ds[0] : 0;
+            int mpos = (int)(r1[1] % (uint32_t)(clen > 1 ? clen : 1));
+            int msub = cs[mpos];
+            if (dlen >= 1 && clen + dlen - msub <= L) {
+                tree_replace((unsigned)L, mpos, 0, dlen, mpos + msub, clen, dlen - msub, cv, ct, cs, dv, dt, ds, ov + oo, ot + oo,
+                             os + oo);
+                continue;
+            }
+        }
+        copy_row((unsigned)L, clen, cv, ct, cs, ov + oo, ot + oo, os + oo);
     }
 }
 

@@ -137,6 +137,69 @@ def generate(pop, gp_len, var_len, out_len, out_prob, const_prob, keys, depth2le
     return v, t, s
 
 
+def generate_philox(pop, gp_len, var_len, out_len, out_prob, const_prob, keys, depth2leaf, roulette, const_samples, nthreads=1):
+    """evogp_generate_philox restated: same growth, Philox4x32-10 counter-based draws."""
+    keys = _c(keys, np.uint32)
+    depth2leaf, roulette = _c(depth2leaf, np.float32), _c(roulette, np.float32)
+    const_samples = _c(const_samples, np.float32)
+    v = np.zeros((pop, gp_len), np.float32)
+    t = np.zeros((pop, gp_len), np.int16)
+    s = np.zeros((pop, gp_len), np.int16)
+    lib().oracle_generate_philox(C.c_uint(pop), C.c_uint(gp_len), C.c_uint(var_len), C.c_uint(out_len),
+                                 C.c_uint(const_samples.shape[0]), C.c_float(out_prob), C.c_float(const_prob),
+                                 _p(keys, u32p), _p(depth2leaf, f32p), _p(roulette, f32p), _p(const_samples, f32p),
+                                 _p(v, f32p), _p(t, i16p), _p(s, i16p), C.c_int(nthreads))
+    return v, t, s
+
+
+def philox(c0, c1, k0, k1):
+    out = np.zeros(4, np.uint32)
+    lib().oracle_philox(C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(k0), C.c_uint32(k1), _p(out, u32p))
+    return out
+
+
+def extract_subtree(value, ntype, size, pos):
+    value, ntype, size = _c(value, np.float32), _c(ntype, np.int16), _c(size, np.int16)
+    pos = _c(pos, np.int32)
+    P, L = value.shape
+    v, t, s = np.zeros_like(value), np.zeros_like(ntype), np.zeros_like(size)
+    lib().oracle_extract_subtree(C.c_int(P), C.c_int(L), _p(value, f32p), _p(ntype, i16p), _p(size, i16p), _p(pos, i32p),
+                                 _p(v, f32p), _p(t, i16p), _p(s, i16p))
+    return v, t, s
+
+
+def tournament(fitness, t_size, best_p, replace, count, keys):
+    fitness, keys = _c(fitness, np.float32), _c(keys, np.uint32)
+    out = np.zeros(count, np.int32)
+    lib().oracle_tournament(C.c_int(fitness.shape[0]), _p(fitness, f32p), C.c_int(t_size), C.c_float(best_p), C.c_int(int(replace)),
+                            C.c_int(count), _p(keys, u32p), _p(out, i32p))
+    return out
+
+
+def feistel_perm(n, round_, keys):
+    keys = _c(keys, np.uint32)
+    out = np.zeros(n, np.uint32)
+    lib().oracle_feistel_perm(C.c_uint32(n), C.c_uint32(round_), _p(keys, u32p), _p(out, u32p))
+    return out
+
+
+def next_generation(value, ntype, size, order, elite, survivors, rate, var_len, out_len, out_prob, const_prob, depth2leaf,
+                    roulette, const_samples, keys, nthreads=1):
+    """evogp_next_generation restated (elitism + crossover + mutation of a whole generation, Philox draws)."""
+    value, ntype, size = _c(value, np.float32), _c(ntype, np.int16), _c(size, np.int16)
+    order = _c(order, np.int64)
+    depth2leaf, roulette, const_samples = _c(depth2leaf, np.float32), _c(roulette, np.float32), _c(const_samples, np.float32)
+    keys = _c(keys, np.uint32)
+    P, L = value.shape
+    v, t, s = np.zeros_like(value), np.zeros_like(ntype), np.zeros_like(size)
+    lib().oracle_next_generation(C.c_int(P), C.c_int(L), _p(value, f32p), _p(ntype, i16p), _p(size, i16p),
+                                 order.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int(elite), C.c_int(survivors), C.c_float(rate),
+                                 C.c_uint(var_len), C.c_uint(out_len), C.c_uint(const_samples.shape[0]), C.c_float(out_prob),
+                                 C.c_float(const_prob), _p(depth2leaf, f32p), _p(roulette, f32p), _p(const_samples, f32p),
+                                 _p(keys, u32p), _p(v, f32p), _p(t, i16p), _p(s, i16p), C.c_int(nthreads))
+    return v, t, s
+
+
 def crossover(value, ntype, size, left_idx, right_idx, left_node, right_node, nthreads=1):
     value, ntype, size = _c(value, np.float32), _c(ntype, np.int16), _c(size, np.int16)
     li, ri, ln, rn = (_c(a, np.int32) for a in (left_idx, right_idx, left_node, right_node))

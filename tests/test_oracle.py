@@ -221,3 +221,30 @@ def test_fitness_matches_batch_forward(orc):
     assert np.array_equal(np.isnan(got), np.isnan(want))
     got2 = orc.sr_fitness(v, t, s, X, y, nthreads=4)
     assert np.array_equal(got, got2, equal_nan=True)
+
+
+def test_philox_known_answer(orc):
+    """Random123 KAT: philox4x32-10, counter 0, key 0 (Salmon et al., SC'11 reference implementation kat_vectors)."""
+    assert [int(x) for x in orc.philox(0, 0, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_own_operator_restatements_are_well_formed(orc):
+    """The restatements of this library's own operators produce structurally valid forests / permutations (their GPU
+    counterparts are compared with them bit for bit in tests/test_gpu_variants.py)."""
+    from conftest import ARITH_FUNCS, depth2leaf, roulette
+    d2l, roul, consts = depth2leaf(5), roulette(ARITH_FUNCS), np.array([-1.0, 0.0, 1.0], np.float32)
+    pv = orc.generate_philox(3000, 64, 3, 1, 0.5, 0.5, np.array([9, 9], np.uint32), d2l, roul, consts)
+    lens = orc.check_forest(*pv, input_len=3)
+    tv = orc.generate(3000, 64, 3, 1, 0.5, 0.5, np.array([9, 9], np.uint32), d2l, roul, consts)
+    assert abs(lens.mean() - tv[2][:, 0].mean()) < 0.1 * tv[2][:, 0].mean()        # same growth distribution
+    order = np.random.default_rng(0).permutation(3000).astype(np.int64)
+    nv = orc.next_generation(*pv, order, 30, 900, 0.3, 3, 1, 0.5, 0.5, depth2leaf(3), roul, consts, np.array([1, 2], np.uint32))
+    orc.check_forest(*nv, input_len=3)
+    assert np.array_equal(nv[1][:30], pv[1][order[:30]])
+    perm = orc.feistel_perm(1001, 2, np.array([3, 4], np.uint32))
+    assert sorted(perm.tolist()) == list(range(1001))
+    fit = np.random.default_rng(1).normal(size=1001).astype(np.float32)
+    w = orc.tournament(fit, 1, 1.0, False, 1001, np.array([3, 4], np.uint32))
+    assert sorted(w.tolist()) == list(range(1001))                                # size-1 tournaments without replacement = a permutation
+    sub = orc.extract_subtree(*pv, np.zeros(3000, np.int32))
+    assert all(np.array_equal(a, b) for a, b in zip(sub, pv))                     # the subtree at the root is the tree
