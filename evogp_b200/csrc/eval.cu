@@ -506,8 +506,8 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
                 err += __shfl_sync(0xffffffffu, prev, 0);
             }
             // forward.cu:478 divides with div.approx (-use_fast_math), and so does this; the accuracy is count / N as torch
-            // computes it (classification.py:66), correctly rounded
-            const float fit = !g.last_tile ? err : (g.mode == MODE_ACC ? __fdiv_rn(err, (float)(unsigned)g.N_total) : err / (float)(unsigned)g.N_total);
+            // computes a tensor / python-scalar division (classification.py:66): count * (1 / N), both correctly rounded
+            const float fit = !g.last_tile ? err : (g.mode == MODE_ACC ? __fmul_rn(err, __frcp_rn((float)(unsigned)g.N_total)) : err / (float)(unsigned)g.N_total);
             if (lane == 0) g.out[tree] = fit;
             // fused all-gather: lane r stores into rank r's buffer over NVLink (peer-mapped memory)
             if (g.peers != nullptr && g.last_tile && lane < g.world) g.peers[lane][g.row_offset + (unsigned)tree] = fit;
