@@ -52,6 +52,11 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
 
 
 
+// Multi-GPU fitness exchange: trees are pushed to the peers in chunks of kPushChunk consecutive trees, by whichever warp
+// finishes a chunk's last tree (tickets are handed out in order, so chunks complete - and travel - while later trees
+// are still being evaluated): 128-byte coalesced stores over NVLink instead of one 4-byte store per tree per peer.
+constexpr int kPushShift = 10, kPushChunk = 1 << kPushShift;
+
 struct ReplayArgs {
     const uint2 *prog;      // [P][Lp]
     unsigned *sched;        // [0] ticket counter
@@ -72,6 +77,7 @@ struct ReplayArgs {
     float *const *peers;
     int world;
     unsigned row_offset;
+    unsigned *chunk_done;   // [ceil(P / kPushChunk)] finished-tree counters (zeroed by the lowering kernel, self-resetting)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -509,8 +515,26 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
             // computes a tensor / python-scalar division (classification.py:66): count * (1 / N), both correctly rounded
             const float fit = !g.last_tile ? err : (g.mode == MODE_ACC ? __fmul_rn(err, __frcp_rn((float)(unsigned)g.N_total)) : err / (float)(unsigned)g.N_total);
             if (lane == 0) g.out[tree] = fit;
-            // fused all-gather: lane r stores into rank r's buffer over NVLink (peer-mapped memory)
-            if (g.peers != nullptr && g.last_tile && lane < g.world) g.peers[lane][g.row_offset + (unsigned)tree] = fit;
+            // fused all-gather over peer-mapped memory (NVLink): the warp that completes a chunk pushes it to every rank
+            if (g.peers != nullptr && g.last_tile) {
+                const int chunk = tree >> kPushShift, first = chunk << kPushShift;
+                const unsigned cnt = (unsigned)min(kPushChunk, g.P - first);
+                unsigned done = 0;
+                if (lane == 0) {
+                    __threadfence();                                           // this tree's fitness is visible before the count
+                    done = atomicAdd(g.chunk_done + chunk, 1u) + 1u;
+                }
+                done = __shfl_sync(0xffffffffu, done, 0);
+                if (done == cnt) {
+                    __threadfence();                                           // ... and every other tree's before the push
+                    const float *src = g.out + first;
+                    for (int r = 0; r < g.world; ++r) {
+                        float *dst = g.peers[r] + g.row_offset + (unsigned)first;
+                        for (unsigned i = lane; i < cnt; i += 32) dst[i] = __ldcg(src + i);
+                    }
+                    if (lane == 0) g.chunk_done[chunk] = 0u;                   // ready for the next launch
+                }
+            }
         }
         __syncwarp();   // every lane is done with prog[buf] before lane 0 re-targets it
         buf ^= 1;
@@ -563,13 +587,16 @@ static inline int prog_pitch(unsigned L) { return (int)((L + 2) & ~1u); }
 struct Workspace {
     uint2 *prog;
     unsigned *sched;   // 64 words
+    unsigned *chunk_done;   // ceil(P / kPushChunk) words behind the programs
 };
+static size_t chunk_words(unsigned P) { return ((size_t)P + kPushChunk - 1) / kPushChunk; }
 static size_t prog_bytes(unsigned P, unsigned L) { return (size_t)P * prog_pitch(L) * sizeof(uint2); }
 static Workspace carve(void *ws, unsigned P, unsigned L) {
     Workspace w;
     unsigned char *b = static_cast<unsigned char *>(ws);
     w.sched = reinterpret_cast<unsigned *>(b);
     w.prog = reinterpret_cast<uint2 *>(b + 256);
+    w.chunk_done = reinterpret_cast<unsigned *>(b + 256 + ((prog_bytes(P, L) + 15) & ~(size_t)15));
     return w;
 }
 
@@ -590,6 +617,7 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.rows_have_sizes = len_stride != 1;
     a.deep_from = deep_from;
     a.fold = g_fold ? 1 : 0;
+    a.chunk_done = w.chunk_done; a.nchunks = (int)chunk_words(P);
     // exactly one resident wave: the kernel strides over the population, so CTAs beyond what the SMs hold at once
     // would only run as a second, half-empty wave (measured: 46 % -> 60 % warps active)
     static thread_local int per_sm_cached = 0, per_sm_dev = -1;
@@ -625,6 +653,7 @@ static int launch_lower_fast(const Workspace &w, unsigned P, unsigned L, unsigne
     a.rows_have_sizes = 1;
     a.deep_from = deep_from;
     a.fold = g_fold ? 1 : 0;
+    a.chunk_done = w.chunk_done; a.nchunks = (int)chunk_words(P);
     static thread_local int per_sm_cached = 0, per_sm_dev = -1;
     if (per_sm_dev != g_props_dev * 4 + NSETS) {
         int n = 0;
@@ -856,6 +885,7 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
     a.P = (int)P; a.Lp = prog_pitch(L); a.N = (int)N; a.V = (int)V; a.O = (int)O;
     a.NP = 0; a.npass = 0; a.depth = depth; a.mode = mode;
     a.peers = scatter.peers; a.world = scatter.world; a.row_offset = scatter.row_offset;
+    a.chunk_done = w.chunk_done;
     a.acc_half = acc_half; a.acc_max = acc_max;
     return multi ? launch_replay<true>(a, depth, choice, st) : launch_replay<false>(a, depth, choice, st);
 }
@@ -907,7 +937,7 @@ extern "C" void evogp_eval_set_timing_events(void *begin_event, void *end_event)
 }
 
 extern "C" size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen) {
-    return 256 + prog_bytes(popSize, maxGPLen);
+    return 256 + ((prog_bytes(popSize, maxGPLen) + 15) & ~(size_t)15) + ((chunk_words(popSize) * 4 + 255) & ~(size_t)255);
 }
 
 extern "C" int evogp_evaluate(unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen, const float *value,

@@ -641,7 +641,14 @@ struct LowerArgs {
     int P, L, Lp, V, O, depth_budget, rows_have_sizes;
     int deep_from;            // SPLIT: slots >= deep_from are addressed with the deep opcodes (program.cuh); else kNoDeepSlots
     int fold;                 // single-output: fold functions of constant leaves into constants
+    unsigned *chunk_done;     // multi-GPU push counters of the replay kernel (eval.cu), zeroed here
+    int nchunks;
 };
+__device__ __forceinline__ void lower_zero_scheduler_words(const LowerArgs &g) {
+    if (blockIdx.x != 0) return;
+    if (threadIdx.x < 64) g.sched[threadIdx.x] = 0;                          // ticket counters of the replay kernel
+    for (int i = threadIdx.x; i < g.nchunks; i += blockDim.x) g.chunk_done[i] = 0;
+}
 
 // one warp per tree, grid-stride over the population
 // SPLIT (single-output only): LOAD + acc-form for operators on leaves (see lower_tree_single)
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const size_t per_warp = (lower_scratch_bytes(g.L) + 15) & ~(size_t)15;
     const LowerScratch k = carve_scratch(lower_smem + warp * per_warp, g.L);
-    if (blockIdx.x == 0 && threadIdx.x < 64) g.sched[threadIdx.x] = 0;     // ticket counters of the replay kernel
+    lower_zero_scheduler_words(g);
     const Lanes ln{lane, 32};
     for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
         // rows_have_sizes == 0 (host path uploads one length per tree): sizes are recomputed from the arities

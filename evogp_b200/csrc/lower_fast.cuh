@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) lower_fast_kernel(LowerArgs g) {
     extern __shared__ __align__(16) unsigned char lower_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     unsigned char *scratch = lower_smem + warp * lower_fast_per_warp<NSETS>(g.L);
-    if (blockIdx.x == 0 && threadIdx.x < 64) g.sched[threadIdx.x] = 0;     // ticket counters of the replay kernel
+    lower_zero_scheduler_words(g);
     for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
         const float *val = g.value + (size_t)n * g.L;
         const int16_t *typ = g.type + (size_t)n * g.L, *srow = g.size + (size_t)n * g.L;
