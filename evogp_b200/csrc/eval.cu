@@ -230,6 +230,41 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
         tstack = tmem_base_slot + ((uint32_t)(warp & 3) * 32u << 16) + (uint32_t)(warp >> 2) * (uint32_t)g.tmem_slots * (uint32_t)K;
     }
 
+    // ---- fused all-gather over peer-mapped memory (NVLink): the warp that completes a chunk of kPushChunk consecutive
+    //      trees pushes it to every rank with coalesced stores.  Completion is counted per chunk; the protocol is software-
+    //      pipelined over this warp's trees so that no round trip is ever waited for: at the end of tree k lane 0
+    //      (1) reads the count returned for tree k-2, (2) fences and counts tree k-1 (its fitness store was issued a whole
+    //      tree ago, so the fence finds it already performed), (3) has just stored the fitness of tree k. ----
+    int ex_stored = -1, ex_counted = -1;     // lane 0: tree whose fitness is stored but not counted / counted, result pending
+    unsigned ex_done = 0;
+    auto exchange_step = [&](int cur) {
+        int push = -1;
+        if (lane == 0) {
+            if (ex_counted >= 0) {
+                const int chunk = ex_counted >> kPushShift;
+                if (ex_done == (unsigned)min(kPushChunk, g.P - (chunk << kPushShift))) push = chunk;
+            }
+            ex_counted = ex_stored;
+            if (ex_stored >= 0) {
+                __threadfence();                                               // that tree's fitness is visible before its count
+                ex_done = atomicAdd(g.chunk_done + (ex_stored >> kPushShift), 1u) + 1u;
+            }
+            ex_stored = cur;
+        }
+        push = __shfl_sync(0xffffffffu, push, 0);
+        if (push >= 0) {
+            __threadfence();                                                   // every counted tree's fitness before the push
+            const int first = push << kPushShift;
+            const unsigned cnt = (unsigned)min(kPushChunk, g.P - first);
+            const float *src = g.out + first;
+            for (int r = 0; r < g.world; ++r) {
+                float *dst = g.peers[r] + g.row_offset + (unsigned)first;
+                for (unsigned i = lane; i < cnt; i += 32) dst[i] = __ldcg(src + i);
+            }
+            if (lane == 0) g.chunk_done[push] = 0u;                            // ready for the next launch
+        }
+    };
+
     const uint32_t row_bytes = (uint32_t)g.Lp * 8u;
     uint32_t phase0 = 0, phase1 = 0;
     int buf = 0;
@@ -515,30 +550,15 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
             // computes a tensor / python-scalar division (classification.py:66): count * (1 / N), both correctly rounded
             const float fit = !g.last_tile ? err : (g.mode == MODE_ACC ? __fmul_rn(err, __frcp_rn((float)(unsigned)g.N_total)) : err / (float)(unsigned)g.N_total);
             if (lane == 0) g.out[tree] = fit;
-            // fused all-gather over peer-mapped memory (NVLink): the warp that completes a chunk pushes it to every rank
-            if (g.peers != nullptr && g.last_tile) {
-                const int chunk = tree >> kPushShift, first = chunk << kPushShift;
-                const unsigned cnt = (unsigned)min(kPushChunk, g.P - first);
-                unsigned done = 0;
-                if (lane == 0) {
-                    __threadfence();                                           // this tree's fitness is visible before the count
-                    done = atomicAdd(g.chunk_done + chunk, 1u) + 1u;
-                }
-                done = __shfl_sync(0xffffffffu, done, 0);
-                if (done == cnt) {
-                    __threadfence();                                           // ... and every other tree's before the push
-                    const float *src = g.out + first;
-                    for (int r = 0; r < g.world; ++r) {
-                        float *dst = g.peers[r] + g.row_offset + (unsigned)first;
-                        for (unsigned i = lane; i < cnt; i += 32) dst[i] = __ldcg(src + i);
-                    }
-                    if (lane == 0) g.chunk_done[chunk] = 0u;                   // ready for the next launch
-                }
-            }
+            if (g.peers != nullptr && g.last_tile) exchange_step(tree);
         }
         __syncwarp();   // every lane is done with prog[buf] before lane 0 re-targets it
         buf ^= 1;
         tree = next;
+    }
+    if (g.peers != nullptr && g.last_tile && g.mode <= MODE_ACC) {   // drain the exchange pipeline
+        exchange_step(-1);
+        exchange_step(-1);
     }
     if constexpr (TSTK) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
