@@ -16,7 +16,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB_SO = os.path.join(LIBDIR, "libevogp_b200.so")
 OPS_SO = os.path.join(LIBDIR, "evogp_cuda_ops.so")
 
-CU_SOURCES = ["runtime.cu", "eval.cu", "splice.cu", "generate.cu", "nextgen.cu", "select.cu", "host_api.cu"]
+CU_SOURCES = ["runtime.cu", "eval.cu", "eval_exchange.cu", "eval_acc.cu", "splice.cu", "generate.cu", "nextgen.cu", "select.cu", "host_api.cu"]
 
 
 def _headers():

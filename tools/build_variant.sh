@@ -16,7 +16,7 @@ mkdir -p "$work/evogp_b200/csrc" "$work/include"
 cp "$ROOT"/evogp_b200/csrc/* "$work/evogp_b200/csrc/"; cp "$ROOT"/include/*.h "$work/include/"
 (cd "$work/evogp_b200/csrc" && env "${envs[@]}" python gen_fastpath.py > /dev/null)
 objs=()
-for f in runtime eval splice generate nextgen select host_api; do
+for f in runtime eval eval_exchange eval_acc splice generate nextgen select host_api; do
   nvcc -O3 -std=c++17 -use_fast_math -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -O3 "${flags[@]}" \
        -c "$work/evogp_b200/csrc/$f.cu" -o "$work/$f.o" 2>/dev/null &
   objs+=("$work/$f.o")

@@ -53,9 +53,19 @@ def main():
     abi.evogp_eval_set_timing_events(None, None)
     step = e0.elapsed_time(e1) / reps
     rep = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(0)
+        for i in range(20):
+            fitness(pops[i % 4])
+        clock = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)     # while the queue is still busy
+        torch.cuda.synchronize()
+    except Exception:
+        clock = None
     f = torch.nan_to_num(fit, nan=0.0, posinf=0.0, neginf=0.0).clamp(max=1e6)
     print(json.dumps({"lib": os.environ.get("EVOGP_B200_LIB", "default"), "config": cfg, "pop": P, "step_us": step * 1e3, "replay_us": rep * 1e3,
-                      "lower_us": (step - rep) * 1e3, "tree_evals_per_s": P * w["N"] / (step * 1e-3),
+                      "lower_us": (step - rep) * 1e3, "sm_mhz": clock, "tree_evals_per_s": P * w["N"] / (step * 1e-3),
                       "fitness_digest": float(f.double().sum()), "env": {k: v for k, v in os.environ.items() if k.startswith("EVOGP_")}}))
 
 
