@@ -61,7 +61,7 @@ def make_config(cfg_id, world):
             "l2": "inputs rotate over %d populations (%.0f MB of rows + %.0f MB of programs per GPU) > 126 MB L2"
                   % (ROTATE, ROTATE * per * w["L"] * 8 / 1e6, per * (w["L"] + 2) * 8 / 1e6),
             "parallelism": "1 GPU" if world == 1 else
-                           "population replicated, evaluation sharded x%d by rows, fitness exchange fused into the evaluation kernel" % world}
+                           "population replicated, evaluation sharded x%d by rows, fitness slices exchanged through peer-mapped symmetric memory" % world}
 
 
 def target_fn(X):
@@ -478,7 +478,7 @@ def hbm_kernel_report(dev, peak):
 
 def config5_loop(dev, world, rank, exch_cls):
     """BASELINE configs[4]: full GP loop, 100 generations, pop 500000, mutation_rate 0.2: every rank evaluates its row
-    shard (fitness exchange fused into the kernel), then runs the identical fused generation step on the replicated
+    shard (fitness exchange over peer memory), then runs the identical fused generation step on the replicated
     population.  Value = P * N * G / t_total (max over ranks)."""
     import torch
     import torch.distributed as dist
@@ -527,7 +527,7 @@ def config5_loop(dev, world, rank, exch_cls):
     return {"value": P * c["N"] * G / t, "unit": "tree-evals/s (P*N*G / t_total)", "generations": G, "ms_per_generation": t / G * 1e3,
             "n_gpus": world, "mean_tree_len_after": float(algo.forest.batch_subtree_size[:, 0].float().mean()),
             "populations_identical_on_all_ranks": same,
-            "what": "pop 500000, V 10, mutation_rate 0.2, selection 0.3 / elite 0.01: sharded evaluation (fused fitness exchange) + "
+            "what": "pop 500000, V 10, mutation_rate 0.2, selection 0.3 / elite 0.01: sharded evaluation (fitness exchange over peer memory) + "
                     "evogp_next_generation (one kernel) + torch.sort per generation; device-timed, max over ranks"}
 
 
@@ -564,8 +564,9 @@ def run_ours(args, out):
 
     exch = FitnessExchange(P_total, dev) if world > 1 else None
     exchange_kind = ("none (1 GPU)" if world == 1 else
-                     ("fused into the evaluation kernel over peer-mapped symmetric memory" if exch.available
-                      else "NCCL all_gather (symmetric memory unavailable: %s)" % exch.why))
+                     ({"push": "evaluation kernel, then evogp_push_fitness: coalesced stores into every rank's buffer over peer-mapped symmetric memory, then one inter-GPU barrier",
+                       "fused": "fused into the evaluation kernel (evogp_SR_fitness_scatter) over peer-mapped symmetric memory"}.get(exch.mode, exch.mode)
+                      if exch.available else "NCCL all_gather (symmetric memory unavailable: %s)" % exch.why))
 
     def step(i):
         if exch is not None:

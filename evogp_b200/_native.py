@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "evogp_version", "evogp_last_error", "evogp_launch_count", "evogp_generate", "evogp_mutate", "evogp_crossover",
     "evogp_eval_workspace_bytes", "evogp_eval_set_timing_events", "evogp_evaluate", "evogp_SR_fitness", "evogp_batch_forward",
     "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation", "evogp_SR_fitness_scatter", "evogp_debug_lower", "evogp_classification_accuracy", "evogp_generate_philox", "evogp_extract_subtree",
-    "evogp_tournament_select",
+    "evogp_tournament_select", "evogp_push_fitness",
 )
 
 
@@ -58,6 +58,8 @@ def abi():
     L.evogp_host_release.restype = None
     L.evogp_next_generation.restype = i
     L.evogp_next_generation.argtypes = [i, i, vp, vp, vp, vp, i, i, f, u, u, u, f, f, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.evogp_push_fitness.restype = i
+    L.evogp_push_fitness.argtypes = [vp, u, vp, u, u, vp]
     L.evogp_generate_philox.restype = i
     L.evogp_generate_philox.argtypes = [u, u, u, u, u, f, f, vp, vp, vp, vp, vp, vp, vp, vp]
     L.evogp_extract_subtree.restype = i

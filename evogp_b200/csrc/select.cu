@@ -138,9 +138,33 @@ __global__ void __launch_bounds__(256) tournament_kernel(TournamentArgs g) {
     g.winners[j] = win;
 }
 
+// ---- multi-GPU: this rank's fitness slice -> every rank's full-population buffer (peer-mapped memory, NVLink) ----
+__global__ void __launch_bounds__(256) push_fitness_kernel(const float *__restrict__ local, unsigned count, float *const *peers,
+                                                           int world, unsigned row_offset) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (int r = 0; r < world; ++r) {
+        float *dst = peers[r] + row_offset;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = local[i];   // 128 B per warp store
+    }
+}
+
 }  // namespace evogp
 
 using namespace evogp;
+
+extern "C" int evogp_push_fitness(const float *local_fitness, unsigned count, float *const *peer_fitnesses, unsigned world,
+                                  unsigned row_offset, void *stream) {
+    EVOGP_REQUIRE(local_fitness != nullptr && peer_fitnesses != nullptr, "pointers must not be NULL");
+    EVOGP_REQUIRE(world >= 1 && world <= 64, "world must be in [1, 64], got %u", world);
+    if (count == 0) return EVOGP_OK;
+    int rc = ensure_device_ok();
+    if (rc) return rc;
+    unsigned grid = (count + 255) / 256;
+    if (grid > 296) grid = 296;
+    push_fitness_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(local_fitness, count, peer_fitnesses, (int)world, row_offset);
+    count_launch();
+    return check_launch("push_fitness");
+}
 
 extern "C" int evogp_extract_subtree(int popSize, int gpLen, const float *value, const int16_t *type,
                                      const int16_t *subtree_size, const int *positions, float *value_res,

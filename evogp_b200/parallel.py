@@ -8,10 +8,10 @@ Populations stay bit-identical across ranks because every genetic kernel is a de
 integer move and every rank consumes identical RNG streams (see `seed_all`).
 
 The exchange itself comes in two forms: `all_gather_fitness` (one NCCL all-gather; gloo in the CPU
-tests) and `FitnessExchange` (NVLink boxes): the evaluation kernel stores every fitness straight
-into each rank's full-population buffer through peer-mapped symmetric memory
-(`evogp_SR_fitness_scatter`), so the all-gather is fused into the kernel and only a ~7 us
-inter-GPU barrier follows it.
+tests) and `FitnessExchange` (NVLink boxes): every rank's fitness slice is written straight into
+each rank's full-population buffer through peer-mapped symmetric memory - by a small kernel of its
+own after the evaluation (`evogp_push_fitness`, the default) or by the evaluation kernel itself
+(`evogp_SR_fitness_scatter`, EVOGP_EXCHANGE=fused) - and a ~7 us inter-GPU barrier follows it.
 """
 import ctypes
 import os
@@ -54,7 +54,7 @@ def seed_all(seed: int):
 
 
 class FitnessExchange:
-    """Fitness all-gather fused into the evaluation kernel over peer-mapped memory.
+    """Fitness all-gather over peer-mapped memory: own kernels, no NCCL collective on the data path.
 
     Two full-population fitness buffers in torch symmetric memory (peer-mapped over NVLink / NVSwitch), used
     alternately: the kernel of generation g stores into buffer g % 2 of every rank while a slower rank may still be
@@ -71,8 +71,14 @@ class FitnessExchange:
         if self.world > 32:
             self.why = "more than 32 ranks"
             return
-        if os.environ.get("EVOGP_FUSED_EXCHANGE", "1") == "0":
-            self.why = "disabled by EVOGP_FUSED_EXCHANGE=0"
+        # EVOGP_EXCHANGE = push (default): plain evaluation kernel, then one small kernel that copies this rank's slice into
+        # every rank's buffer over peer memory; fused: the evaluation kernel itself pushes finished chunks
+        # (evogp_SR_fitness_scatter); nccl: one all-gather.  Measured at 2 x B200, 500000 trees per rank: the fused
+        # form costs +0.21 ms per step (fence + counter per tree, and the protocol's code next to the replay loop in the
+        # instruction cache), the push kernel ~0.01 ms.
+        self.mode = os.environ.get("EVOGP_EXCHANGE", "push")
+        if os.environ.get("EVOGP_FUSED_EXCHANGE", "1") == "0" or self.mode == "nccl":
+            self.why = "disabled by EVOGP_EXCHANGE=nccl"
             return
         try:
             if dist.get_backend(group) != "nccl":
@@ -110,6 +116,16 @@ class FitnessExchange:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             local = torch.empty(P, dtype=torch.float32, device=dev)
             vp = lambda t: ctypes.c_void_p(t.data_ptr())
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if self.mode != "fused":
+                rc = abi.evogp_SR_fitness(P, N, L, V, O, 1 if use_MSE else 0, vp(shard.batch_node_value), vp(shard.batch_node_type),
+                                          vp(shard.batch_subtree_size), vp(datapoints.contiguous()), vp(labels.contiguous()),
+                                          vp(local), 4, vp(ws), ctypes.c_size_t(ws_bytes), stream)
+                _native.check(rc, "evogp_SR_fitness")
+                rc = abi.evogp_push_fitness(vp(local), P, ctypes.c_void_p(hdl.buffer_ptrs_dev), self.world, self.lo, stream)
+                _native.check(rc, "evogp_push_fitness")
+                hdl.barrier(channel=0)
+                return buf
             rc = abi.evogp_SR_fitness_scatter(P, N, L, V, O, 1 if use_MSE else 0, vp(shard.batch_node_value),
                                               vp(shard.batch_node_type), vp(shard.batch_subtree_size),
                                               vp(datapoints.contiguous()), vp(labels.contiguous()), vp(local),

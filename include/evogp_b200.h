@@ -125,6 +125,13 @@ int evogp_SR_fitness_scatter(unsigned popSize, unsigned dataPoints, unsigned gpL
                              float *const *peer_fitnesses, unsigned world, unsigned row_offset, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* The exchange of evogp_SR_fitness_scatter as a kernel of its own: copies this rank's fitness slice local_fitness[count]
+ * into EVERY rank's full-population buffer at [row_offset, row_offset + count) through peer-mapped memory (coalesced
+ * 128-byte stores over NVLink).  Measured on B200s this costs less than carrying the exchange protocol
+ * inside the evaluation kernel, so parallel.FitnessExchange uses it by default.  Arguments as evogp_SR_fitness_scatter. */
+int evogp_push_fitness(const float *local_fitness, unsigned count, float *const *peer_fitnesses, unsigned world,
+                       unsigned row_offset, void *stream);
+
 /* Fused form of Forest.batch_forward (tree/forest.py:143-176), which the reference
  * implements by replicating the forest dataPoints times: results[P, N, O]. */
 int evogp_batch_forward(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
