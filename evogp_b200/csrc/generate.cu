@@ -15,6 +15,7 @@
 //   * subtree sizes need no stack either: scanning the prefix backwards,
 //     size[i] = 1 + size[c1] + size[c2] + ... with c1 = i+1, c2 = c1 + size[c1];
 //   * rows leave the SM through warp-cooperative, coalesced, zero-filled stores.
+#include <cstdlib>
 #include "gen_tree.cuh"
 
 namespace evogp {
@@ -103,6 +104,177 @@ __global__ void __launch_bounds__(128) generate_kernel(GenArgs g) {
 
 using namespace evogp;
 
+// ---------------------------------------------------------------------------
+// generate_fast_kernel — the taus88 mode at full residency.
+//
+// generate_kernel above is bound by its own shape: 8 bytes of shared memory per node slot cap it at 12 warps per SM, the
+// roulette is scanned downwards entry by entry (~25 iterations per function node with four functions in use), every
+// lane's function / leaf branch serialises the warp, and one thread per tree walks the row backwards again for the
+// subtree sizes (154 us for 100000 trees = 5 % of the HBM roofline for the 51 MB it writes, BENCH r2).  Same draws,
+// same trees (tests/test_gpu_parity.py::test_generate_bit_exact, tests/golden), different everything else:
+//   * a node is ONE 32-bit word in shared memory (16-bit value code: variable index / constant-sample index / function
+//     id [| out index << 5]; 3-bit type + out flag; 11-bit size) -> 24+ warps per SM; values are decoded at write-out;
+//   * the body of the growth loop is branch-free: the draws a leaf needs beyond a function's are made speculatively and
+//     the generator state is committed with selects; the roulette is a 5-step binary search (it is a cumulative sum;
+//     a non-monotone table, possible through the raw-tensor argument, keeps the reference's downward scan);
+//   * subtree sizes are finalised as frames pop (a frame's function node spans [start, cnt)), no second pass;
+//   * each warp writes its own 32 rows as soon as its longest tree is done (no CTA barrier).
+// ---------------------------------------------------------------------------
+struct Taus88State {
+    uint32_t z1, z2, z3;
+};
+__device__ __forceinline__ uint32_t taus88_step(Taus88State &s) {
+    uint32_t b;
+    b = ((s.z1 << 13) ^ s.z1) >> 19;
+    s.z1 = ((s.z1 & 0xFFFFFFFEu) << 12) ^ b;
+    b = ((s.z2 << 2) ^ s.z2) >> 25;
+    s.z2 = ((s.z2 & 0xFFFFFFF8u) << 4) ^ b;
+    b = ((s.z3 << 3) ^ s.z3) >> 11;
+    s.z3 = ((s.z3 & 0xFFFFFFF0u) << 17) ^ b;
+    return s.z1 ^ s.z2 ^ s.z3;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return __uint2float_rn(x) * 2.3283064365386963e-10f; }   // float(u32) / 2^32
+
+constexpr uint32_t kGenOutFlag = 8u;   // bit 3 of the packed type field
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
+    extern __shared__ uint32_t gsm[];
+    __shared__ float s_leaf[16];
+    __shared__ float s_roul[32];
+    __shared__ int s_mono;
+    const int pitch = g.pitch, L = (int)g.L;
+    if (threadIdx.x < 16) s_leaf[threadIdx.x] = threadIdx.x < kMaxFullDepth ? g.depth2leaf[threadIdx.x] : 2.0f;   // depth >= 10: a leaf (the reference reads out of bounds there)
+    if (threadIdx.x < 32) s_roul[threadIdx.x] = threadIdx.x < F_END ? g.roulette[threadIdx.x] : __int_as_float(0x7f800000);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mono = 1;
+        for (int i = 1; i < F_END; ++i) mono &= s_roul[i] >= s_roul[i - 1];
+        s_mono = mono;
+    }
+    __syncthreads();
+    const bool mono = s_mono != 0;
+    const int lane = threadIdx.x & 31;
+    uint32_t *row = gsm + (size_t)threadIdx.x * pitch;
+    const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t V = g.V, S = g.S, O = g.O;
+
+    int cnt = 0, d = n < g.P ? 0 : -1;
+    uint64_t owed = 1;                 // children still owed per depth, 4 bits each; root frame {1, 0}
+    uint64_t start_lo = 0, start_hi = 0;   // index of the function node that opened the frame of depth 1..5 / 6..10, 12 bits each
+    Taus88State st;
+    st.z1 = st.z2 = st.z3 = tree_seed(n, g.keys[0], g.keys[1]);
+    while (d >= 0 && cnt < L) {
+        owed -= 1ull << (4 * d);                                   // cd.childs-- (generate.cu:61)
+        const float leafp = s_leaf[d];
+        // draws: u (leaf test); then r (function) / u (constant test); then a raw word (leaf) / u (out test, multi);
+        // then a raw word (out index, multi).  All made, the state a path did not reach is dropped.
+        Taus88State s1 = st;
+        const uint32_t o1 = taus88_step(s1);
+        Taus88State s2 = s1;
+        const uint32_t o2 = taus88_step(s2);
+        Taus88State s3 = s2;
+        const uint32_t o3 = taus88_step(s3);
+        const bool is_func = u32_to_unit(o1) >= leafp;             // :71
+        const float r = u32_to_unit(o2);
+        int k = 0;                                                 // number of roulette entries <= r (:74-84)
+        if (mono) {
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s_roul[k + step - 1] <= r) k += step;
+        } else {
+            for (int i = F_END - 1; i >= 0; --i)
+                if (r >= s_roul[i]) { k = i + 1; break; }
+        }
+        const uint32_t ftype = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
+        const bool is_const = r <= g.constProb;                    // the same second draw, read as the constant test (:109)
+        const uint32_t m = is_const ? S : V;
+        uint32_t code = is_func ? (uint32_t)k : o3 % m, type = is_func ? ftype : (is_const ? NT_CONST : NT_VAR);
+        Taus88State next = is_func ? s2 : s3;
+        if constexpr (MULTI) {
+            Taus88State s4 = s3;
+            const uint32_t o4 = taus88_step(s4);
+            const bool is_out = is_func && u32_to_unit(o3) <= g.outProb;   // :88-96
+            if (is_func) next = is_out ? s4 : s3;
+            if (is_out) {
+                code |= (o4 % O) << 5;
+                type |= kGenOutFlag;
+            }
+        }
+        st = next;
+        row[cnt] = (code << 16) | type | (is_func ? 0u : (1u << 4));      // a leaf is a subtree of size 1
+        const int arity = is_func ? (int)ftype - 1 : 0;
+        if (arity > 0) {                                           // open the frame of its children
+            ++d;
+            owed |= (uint64_t)arity << (4 * d);
+            const int sh = 12 * ((d - 1) % 5);
+            if (d <= 5) start_lo = (start_lo & ~(0xFFFull << sh)) | ((uint64_t)cnt << sh);
+            else start_hi = (start_hi & ~(0xFFFull << sh)) | ((uint64_t)cnt << sh);
+            ++cnt;
+        } else {
+            ++cnt;
+            while (d >= 0 && ((owed >> (4 * d)) & 0xF) == 0) {      // frames whose children are all there: their node is complete
+                if (d > 0) {
+                    const int sh = 12 * ((d - 1) % 5);
+                    const int at = (int)(((d <= 5 ? start_lo : start_hi) >> sh) & 0xFFF);
+                    row[at] |= (uint32_t)(cnt - at) << 4;
+                }
+                --d;
+            }
+        }
+    }
+    for (; d > 0; --d) {   // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open
+        const int sh = 12 * ((d - 1) % 5);
+        const int at = (int)(((d <= 5 ? start_lo : start_hi) >> sh) & 0xFFF);
+        row[at] |= (uint32_t)(cnt - at) << 4;
+    }
+    const int len = cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
+    __syncwarp();
+
+    // ---- this warp's 32 rows leave through coalesced, zero-filled stores ----
+    const unsigned first = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    const uint32_t *rows = gsm + (size_t)(threadIdx.x & ~31) * pitch;
+    auto decode = [&](uint32_t w, uint32_t &v, uint32_t &t, uint32_t &sz) {
+        const uint32_t code = w >> 16, ty = w & 7u;
+        t = ty | ((w & kGenOutFlag) ? (uint32_t)NT_OUT : 0u);
+        sz = (w >> 4) & 0xFFFu;
+        if (ty == NT_CONST) v = __float_as_uint(__ldg(g.consts + code));
+        else if (ty == NT_VAR) v = __float_as_uint((float)code);
+        else if (MULTI && (w & kGenOutFlag)) v = (code & 31u) | ((code >> 5) << 16);      // kernel.h:105-113
+        else v = __float_as_uint((float)(code & 31u));
+    };
+    for (int r = 0; r < 32; ++r) {
+        const unsigned tree = first + r;
+        if (tree >= g.P) break;
+        const int rl = __shfl_sync(0xffffffffu, len, r);
+        const uint32_t *src = rows + (size_t)r * pitch;
+        float *ov = g.ovalue + (size_t)tree * L;
+        int16_t *ot = g.otype + (size_t)tree * L;
+        int16_t *os = g.osize + (size_t)tree * L;
+        if ((L & 1) == 0) {
+            for (int j = lane * 2; j < L; j += 64) {
+                uint32_t v0 = 0, t0 = 0, z0 = 0, v1 = 0, t1 = 0, z1 = 0;
+                if (j < rl) decode(src[j], v0, t0, z0);
+                if (j + 1 < rl) decode(src[j + 1], v1, t1, z1);
+                *reinterpret_cast<uint2 *>(ov + j) = make_uint2(v0, v1);
+                *reinterpret_cast<uint32_t *>(ot + j) = t0 | (t1 << 16);
+                *reinterpret_cast<uint32_t *>(os + j) = z0 | (z1 << 16);
+            }
+        } else {
+            for (int j = lane; j < L; j += 32) {
+                uint32_t v = 0, t = 0, z = 0;
+                if (j < rl) decode(src[j], v, t, z);
+                ov[j] = __uint_as_float(v);
+                ot[j] = (int16_t)t;
+                os[j] = (int16_t)z;
+            }
+        }
+    }
+}
+
+// EVOGP_GENERATE_FAST=0 keeps the one-size-fits-all kernel (the A/B switch of profiles/; default on)
+static const bool g_generate_fast = []() { const char *e = getenv("EVOGP_GENERATE_FAST"); return !(e && e[0] == '0'); }();
+
 static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
                          unsigned constSamplesLen, float outProb, float constProb, const unsigned *keys,
                          const float *depth2leafProbs, const float *rouletteFuncs, const float *constSamples,
@@ -122,6 +294,28 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
     a.ovalue = value_res; a.otype = type_res; a.osize = subtree_size_res;
     a.P = popSize; a.L = maxGPLen; a.V = varLen; a.O = outLen; a.S = constSamplesLen;
     a.outProb = outProb; a.constProb = constProb;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the packed-word kernel: taus88 mode, codes that fit 16 bits (variable / constant-sample index, out index << 5)
+    if (!philox && g_generate_fast && varLen <= 65535 && constSamplesLen <= 65535 && outLen <= 1024) {
+        a.pitch = (int)(maxGPLen | 1u);                            // words per row, odd
+        int lanes = (int)((200 * 1024) / ((size_t)a.pitch * 4) / 3);   // three CTAs per SM
+        lanes = lanes >= 256 ? 256 : (lanes / 32) * 32;
+        if (lanes < 32) lanes = (size_t)a.pitch * 4 * 32 <= 220 * 1024 ? 32 : 0;
+        if (lanes >= 32) {
+            a.trees_per_block = lanes;
+            const size_t smem = (size_t)lanes * a.pitch * 4;
+            const unsigned grid = (popSize + lanes - 1) / lanes;
+            if (outLen > 1) {
+                EVOGP_CUDA(cudaFuncSetAttribute(generate_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                generate_fast_kernel<true><<<grid, lanes, smem, st>>>(a);
+            } else {
+                EVOGP_CUDA(cudaFuncSetAttribute(generate_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                generate_fast_kernel<false><<<grid, lanes, smem, st>>>(a);
+            }
+            count_launch();
+            return check_launch("generate");
+        }
+    }
     a.pitch = (int)(maxGPLen | 1u) + ((maxGPLen & 1u) ? 2 : 0);   // odd and > L
     const size_t per_tree = (size_t)a.pitch * 8;
     int T = (int)((192 * 1024) / per_tree);
@@ -131,7 +325,6 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
     const int threads = ((T + 31) / 32) * 32;
     const size_t smem = per_tree * T;
     const unsigned grid = (popSize + T - 1) / T;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto launch = [&](auto kern) -> int {
         EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(a);
