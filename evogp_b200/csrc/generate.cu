@@ -31,6 +31,7 @@ struct GenArgs {
     unsigned P, L, V, O, S;
     float outProb, constProb;
     int trees_per_block, pitch;
+    unsigned long long magicV, magicS;   // floor(2^64 / V) + 1, floor(2^64 / S) + 1 (generate_fast_kernel's fastmod)
 };
 
 template <bool MULTI, bool PHILOX>
@@ -112,12 +113,14 @@ using namespace evogp;
 // lane's function / leaf branch serialises the warp, and one thread per tree walks the row backwards again for the
 // subtree sizes (154 us for 100000 trees = 5 % of the HBM roofline for the 51 MB it writes, BENCH r2).  Same draws,
 // same trees (tests/test_gpu_parity.py::test_generate_bit_exact, tests/golden), different everything else:
-//   * a node is ONE 32-bit word in shared memory (16-bit value code: variable index / constant-sample index / function
-//     id [| out index << 5]; 3-bit type + out flag; 11-bit size) -> 24+ warps per SM; values are decoded at write-out;
+//   * a node is ONE 32-bit word in shared memory (variable / constant-sample index or function id, 3-bit type, 12-bit
+//     size) -> 24 warps per SM at max_tree_len 64; values are decoded at write-out;
 //   * the body of the growth loop is branch-free: the draws a leaf needs beyond a function's are made speculatively and
 //     the generator state is committed with selects; the roulette is a 5-step binary search (it is a cumulative sum;
 //     a non-monotone table, possible through the raw-tensor argument, keeps the reference's downward scan);
-//   * subtree sizes are finalised as frames pop (a frame's function node spans [start, cnt)), no second pass;
+//   * subtree sizes are finalised as frames pop (a frame's function node spans [start, cnt); the open frames are a
+//     linked list threaded through the spare bits of the function words), no second pass; the frame counters are
+//     2 bits per depth in one 32-bit register; `raw % V` / `raw % S` use precomputed 64-bit reciprocals;
 //   * each warp writes its own 32 rows as soon as its longest tree is done (no CTA barrier).
 // ---------------------------------------------------------------------------
 struct Taus88State {
@@ -135,9 +138,12 @@ __device__ __forceinline__ uint32_t taus88_step(Taus88State &s) {
 }
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return __uint2float_rn(x) * 2.3283064365386963e-10f; }   // float(u32) / 2^32
 
-constexpr uint32_t kGenOutFlag = 8u;   // bit 3 of the packed type field
+// x % d for a divisor known before the loop: Lemire's fastmod, M = floor(2^64 / d) + 1 computed on the host
+__device__ __forceinline__ uint32_t fastmod_u32(uint32_t x, uint64_t M, uint32_t d) {
+    return (uint32_t)__umul64hi(M * x, (uint64_t)d);
+}
 
-template <bool MULTI>
+// single-output trees (out_len == 1; multi-output populations keep generate_kernel)
 __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     extern __shared__ uint32_t gsm[];
     __shared__ float s_leaf[16];
@@ -157,18 +163,22 @@ __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     const int lane = threadIdx.x & 31;
     uint32_t *row = gsm + (size_t)threadIdx.x * pitch;
     const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t V = g.V, S = g.S, O = g.O;
+    const uint32_t V = g.V, S = g.S;
+    const uint64_t MV = g.magicV, MS = g.magicS;
+    const float constProb = g.constProb;
 
+    // Node word: [2:0] type, [15:4] subtree size, [31:16] variable / constant-sample index (leaves); functions keep their
+    // id in [20:16] and, while their frame is open, the index of the enclosing function node in [31:21].
     int cnt = 0, d = n < g.P ? 0 : -1;
-    uint64_t owed = 1;                 // children still owed per depth, 4 bits each; root frame {1, 0}
-    uint64_t start_lo = 0, start_hi = 0;   // index of the function node that opened the frame of depth 1..5 / 6..10, 12 bits each
+    uint32_t owed = 1;                 // children still owed per depth, 2 bits each (arity <= 3); root frame {1, 0}
+    uint32_t cur = 0;                  // the function node whose children are being generated (depth >= 1)
     Taus88State st;
     st.z1 = st.z2 = st.z3 = tree_seed(n, g.keys[0], g.keys[1]);
     while (d >= 0 && cnt < L) {
-        owed -= 1ull << (4 * d);                                   // cd.childs-- (generate.cu:61)
+        owed -= 1u << (2 * d);                                     // cd.childs-- (generate.cu:61)
         const float leafp = s_leaf[d];
-        // draws: u (leaf test); then r (function) / u (constant test); then a raw word (leaf) / u (out test, multi);
-        // then a raw word (out index, multi).  All made, the state a path did not reach is dropped.
+        // draws: u (leaf test); then r (roulette) or u (constant test) - the same word; then, for a leaf only, a raw word.
+        // All three are made; a function commits the state after two.
         Taus88State s1 = st;
         const uint32_t o1 = taus88_step(s1);
         Taus88State s2 = s1;
@@ -187,46 +197,34 @@ __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
                 if (r >= s_roul[i]) { k = i + 1; break; }
         }
         const uint32_t ftype = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
-        const bool is_const = r <= g.constProb;                    // the same second draw, read as the constant test (:109)
-        const uint32_t m = is_const ? S : V;
-        uint32_t code = is_func ? (uint32_t)k : o3 % m, type = is_func ? ftype : (is_const ? NT_CONST : NT_VAR);
-        Taus88State next = is_func ? s2 : s3;
-        if constexpr (MULTI) {
-            Taus88State s4 = s3;
-            const uint32_t o4 = taus88_step(s4);
-            const bool is_out = is_func && u32_to_unit(o3) <= g.outProb;   // :88-96
-            if (is_func) next = is_out ? s4 : s3;
-            if (is_out) {
-                code |= (o4 % O) << 5;
-                type |= kGenOutFlag;
-            }
-        }
-        st = next;
-        row[cnt] = (code << 16) | type | (is_func ? 0u : (1u << 4));      // a leaf is a subtree of size 1
-        const int arity = is_func ? (int)ftype - 1 : 0;
-        if (arity > 0) {                                           // open the frame of its children
+        const bool is_const = r <= constProb;                      // :109
+        const uint32_t idx = is_const ? fastmod_u32(o3, MS, S) : fastmod_u32(o3, MV, V);
+        st.z1 = is_func ? s2.z1 : s3.z1;
+        st.z2 = is_func ? s2.z2 : s3.z2;
+        st.z3 = is_func ? s2.z3 : s3.z3;
+        if (is_func) {                                             // open the frame of its children
+            row[cnt] = ((uint32_t)k << 16) | (cur << 21) | ftype;
+            cur = (uint32_t)cnt;
             ++d;
-            owed |= (uint64_t)arity << (4 * d);
-            const int sh = 12 * ((d - 1) % 5);
-            if (d <= 5) start_lo = (start_lo & ~(0xFFFull << sh)) | ((uint64_t)cnt << sh);
-            else start_hi = (start_hi & ~(0xFFFull << sh)) | ((uint64_t)cnt << sh);
+            owed |= (ftype - 1u) << (2 * d);
             ++cnt;
         } else {
+            row[cnt] = (idx << 16) | (1u << 4) | (is_const ? (uint32_t)NT_CONST : (uint32_t)NT_VAR);
             ++cnt;
-            while (d >= 0 && ((owed >> (4 * d)) & 0xF) == 0) {      // frames whose children are all there: their node is complete
+            while (d >= 0 && ((owed >> (2 * d)) & 3u) == 0u) {      // frames whose children are all there: their node is complete
                 if (d > 0) {
-                    const int sh = 12 * ((d - 1) % 5);
-                    const int at = (int)(((d <= 5 ? start_lo : start_hi) >> sh) & 0xFFF);
-                    row[at] |= (uint32_t)(cnt - at) << 4;
+                    const uint32_t w = row[cur];
+                    row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
+                    cur = w >> 21;
                 }
                 --d;
             }
         }
     }
     for (; d > 0; --d) {   // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open
-        const int sh = 12 * ((d - 1) % 5);
-        const int at = (int)(((d <= 5 ? start_lo : start_hi) >> sh) & 0xFFF);
-        row[at] |= (uint32_t)(cnt - at) << 4;
+        const uint32_t w = row[cur];
+        row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
+        cur = w >> 21;
     }
     const int len = cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
     __syncwarp();
@@ -235,13 +233,10 @@ __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     const unsigned first = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
     const uint32_t *rows = gsm + (size_t)(threadIdx.x & ~31) * pitch;
     auto decode = [&](uint32_t w, uint32_t &v, uint32_t &t, uint32_t &sz) {
-        const uint32_t code = w >> 16, ty = w & 7u;
-        t = ty | ((w & kGenOutFlag) ? (uint32_t)NT_OUT : 0u);
+        t = w & 7u;
         sz = (w >> 4) & 0xFFFu;
-        if (ty == NT_CONST) v = __float_as_uint(__ldg(g.consts + code));
-        else if (ty == NT_VAR) v = __float_as_uint((float)code);
-        else if (MULTI && (w & kGenOutFlag)) v = (code & 31u) | ((code >> 5) << 16);      // kernel.h:105-113
-        else v = __float_as_uint((float)(code & 31u));
+        const uint32_t code = w >> 16;
+        v = t == NT_CONST ? __float_as_uint(__ldg(g.consts + code)) : __float_as_uint((float)(t == NT_VAR ? code : (code & 31u)));
     };
     for (int r = 0; r < 32; ++r) {
         const unsigned tree = first + r;
@@ -296,7 +291,9 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
     a.outProb = outProb; a.constProb = constProb;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the packed-word kernel: taus88 mode, codes that fit 16 bits (variable / constant-sample index, out index << 5)
-    if (!philox && g_generate_fast && varLen <= 65535 && constSamplesLen <= 65535 && outLen <= 1024) {
+    if (!philox && g_generate_fast && outLen == 1 && varLen <= 65535 && constSamplesLen <= 65535 && maxGPLen <= 1024) {
+        a.magicV = ~0ull / varLen + 1ull;
+        a.magicS = ~0ull / constSamplesLen + 1ull;
         a.pitch = (int)(maxGPLen | 1u);                            // words per row, odd
         int lanes = (int)((200 * 1024) / ((size_t)a.pitch * 4) / 3);   // three CTAs per SM
         lanes = lanes >= 256 ? 256 : (lanes / 32) * 32;
@@ -305,13 +302,8 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
             a.trees_per_block = lanes;
             const size_t smem = (size_t)lanes * a.pitch * 4;
             const unsigned grid = (popSize + lanes - 1) / lanes;
-            if (outLen > 1) {
-                EVOGP_CUDA(cudaFuncSetAttribute(generate_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                generate_fast_kernel<true><<<grid, lanes, smem, st>>>(a);
-            } else {
-                EVOGP_CUDA(cudaFuncSetAttribute(generate_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                generate_fast_kernel<false><<<grid, lanes, smem, st>>>(a);
-            }
+            EVOGP_CUDA(cudaFuncSetAttribute(generate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            generate_fast_kernel<<<grid, lanes, smem, st>>>(a);
             count_launch();
             return check_launch("generate");
         }
