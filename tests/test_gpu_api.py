@@ -346,3 +346,40 @@ def test_classification_accuracy_is_fused(native, orc, O, N, L, funcs):
     assert close.float().mean().item() >= 0.98
     # NaN / inf outputs predict class 0 (softmax turns the whole row NaN); a NaN single output matches nothing
     assert torch.isfinite(got).all() and (got >= 0).all() and (got <= 1).all()
+
+
+# --------------------------------------------------------------------------- Pareto front
+def test_pareto_front_matches_the_reference_formulation(api, orc):
+    """ParetoFront.update is a segmented arg-max by tree size (scatter_reduce); the reference builds an [L, P] masked matrix
+    and takes torch.max over it (genetic_programming.py:65-99).  Same fitness per size, same winning trees, over several
+    generations of updates, NaN fitness included."""
+    tree, algorithm, _, _ = api
+    L, P = 32, 4000
+    rng = np.random.default_rng(7)
+    pf = algorithm.ParetoFront(L, (L, 3, 1))
+    ref_fit = torch.full((L,), float("-inf"), device=G.dev())
+    ref_sol = [torch.zeros((L, L), dtype=dt, device=G.dev()) for dt in (torch.float32, torch.int16, torch.int16)]
+    ref_sol[1][:, 0] = 1; ref_sol[2][:, 0] = 1                                  # Forest.zero_generate: node 0 = CONST 0, size 1
+    for gen in range(5):
+        v, t, s = make_forest(orc, P, L, 3, 1, ["+", "-", "*", "/"], 5, keys=(gen, 3))
+        fit = rng.normal(size=P).astype(np.float32) + 0.3 * gen
+        fit[rng.integers(0, P, 40)] = np.nan
+        dv, dt_, ds, dfit = G.to_dev(v, t, s, fit)
+        forest = tree.Forest(3, 1, dv, dt_, ds)
+        pf.update(dfit, forest)
+        # the reference's formulation, verbatim in spirit: [L, P] masked fitness, max over the population
+        f_use = torch.where(torch.isnan(dfit), torch.full_like(dfit, float("-inf")), dfit)      # the pipeline maps NaN to -inf (standard.py:43)
+        size = ds[:, 0].long()
+        masked = torch.where(size[None, :] == torch.arange(L, device=G.dev())[:, None], f_use[None, :], torch.tensor(float("-inf"), device=G.dev()))
+        best, idx = torch.max(masked, dim=1)
+        better = best > ref_fit
+        ref_fit = torch.where(better, best, ref_fit)
+        for k, src in enumerate((dv, dt_, ds)):
+            ref_sol[k] = torch.where(better[:, None], src[idx], ref_sol[k])
+        assert torch.equal(pf.fitness, ref_fit), f"generation {gen}: per-size best fitness differs"
+        # and the same trees (both formulations keep the FIRST individual that reaches the best fitness of its size)
+        have = torch.isfinite(pf.fitness)
+        assert torch.equal(pf.solution.batch_subtree_size[:, 0].long()[have], torch.arange(L, device=G.dev())[have])
+        for got, want in zip((pf.solution.batch_node_value, pf.solution.batch_node_type, pf.solution.batch_subtree_size), ref_sol):
+            assert torch.equal(got[have], want[have])
+    assert torch.isfinite(pf.fitness).sum() > 5
