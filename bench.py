@@ -654,7 +654,10 @@ def run_ours(args, out):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = P_total * N * args.steps / float(e2e_t)
-    h2d = (hi - lo) * (L * 6 + 2) + N * (V + O) * 4      # value + type rows, one length per tree, dataset
+    # what evogp_SR_fitness_host actually uploads: valid prefixes of node_value + node_type (6 B per node), one 32-bit
+    # offset per tree, the dataset
+    nodes = int(sum(int(p.batch_subtree_size[:, 0].long().sum()) for p in pops[:R2]) // R2)
+    h2d = nodes * 6 + (hi - lo + 9) * 4 + N * (V + O) * 4
     d2h = (hi - lo) * 4
     fit_host_check = float(np.nanmean(np.clip(np.nan_to_num(hfit.numpy(), nan=0.0, posinf=0.0, neginf=0.0), None, 1e6)))
     del hv, ht, hs
@@ -694,7 +697,7 @@ def run_ours(args, out):
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": w["scaling"],
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(cfg_id, world),
                 "e2e": {"value": e2e_value, "unit": "tree-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "path": "evogp_SR_fitness_host (C ABI, pinned host buffers, chunked copy/compute overlap), every rank on its shard"},
+                        "path": "evogp_SR_fitness_host (C ABI, pinned host buffers: valid prefixes packed by a host thread pool, chunked copy/compute overlap), every rank on its shard"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "replay_kernel", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak,

@@ -97,7 +97,8 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
     a.value = value; a.type = type; a.size = size;
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
-    a.rows_have_sizes = len_stride != 1;
+    a.rows_have_sizes = len_stride > 1;                       // 1: one length per tree; 0: compact rows, `size` is the offsets array
+    a.offsets = len_stride == 0 ? reinterpret_cast<const unsigned *>(size) : nullptr;
     a.deep_from = deep_from;
     a.fold = g_fold ? 1 : 0;
     a.chunk_done = w.chunk_done; a.nchunks = (int)chunk_words(P);
@@ -134,6 +135,7 @@ static int launch_lower_fast(const Workspace &w, unsigned P, unsigned L, unsigne
     a.prog = w.prog; a.sched = w.sched;
     a.P = (int)P; a.L = (int)L; a.Lp = prog_pitch(L); a.V = (int)V; a.O = (int)O; a.depth_budget = depth;
     a.rows_have_sizes = 1;
+    a.offsets = nullptr;
     a.deep_from = deep_from;
     a.fold = g_fold ? 1 : 0;
     a.chunk_done = w.chunk_done; a.nchunks = (int)chunk_words(P);
@@ -159,7 +161,7 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
                         cudaStream_t st) {
     if constexpr (!MULTI) {
         if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
-        if (g_lower_fast && len_stride != 1 && L <= 64)
+        if (g_lower_fast && len_stride > 1 && L <= 64)
             return L <= 32 ? launch_lower_fast<1>(w, P, L, V, O, value, type, size, depth, deep_from, st)
                            : launch_lower_fast<2>(w, P, L, V, O, value, type, size, depth, deep_from, st);
     }
@@ -257,7 +259,16 @@ int run_eval(int mode, unsigned P, unsigned N, unsigned L, unsigned V, unsigned 
 
 using namespace evogp;
 
-// internal (host_api.cu): SR fitness with tree lengths given as a compact int16[popSize] array
+// internal (host_api.cu): SR fitness over a COMPACT forest - valid prefixes of value / type back to back, tree n at
+// [offsets[n], offsets[n + 1]) - as the host path uploads it
+int evogp_sr_fitness_packed(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen, int useMSE,
+                            const float *value, const int16_t *type, const unsigned *offsets, const float *variables,
+                            const float *labels, float *fitnesses, void *workspace, size_t workspace_bytes, void *stream) {
+    return run_eval(useMSE ? MODE_MSE : MODE_ABS, popSize, dataPoints, gpLen, varLen, outLen, value, type,
+                    reinterpret_cast<const int16_t *>(offsets), 0, variables, labels, fitnesses, workspace, workspace_bytes, stream);
+}
+
+// internal: SR fitness with tree lengths given as a compact int16[popSize] array
 int evogp_sr_fitness_compact_len(unsigned popSize, unsigned dataPoints, unsigned gpLen, unsigned varLen, unsigned outLen,
                                  int useMSE, const float *value, const int16_t *type, const int16_t *lengths,
                                  const float *variables, const float *labels, float *fitnesses, void *workspace,

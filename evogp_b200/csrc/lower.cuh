@@ -636,6 +636,7 @@ struct LowerArgs {
     const float *value;
     const int16_t *type;
     const int16_t *size;      // packed subtree_size rows [P][L], or (rows_have_sizes == 0) one length per tree
+    const unsigned *offsets;  // non-null: value / type hold valid prefixes back to back, tree n at [offsets[n], offsets[n + 1])
     uint2 *prog;              // [P][Lp]
     unsigned *sched;          // 64 scheduler words, zeroed here (the replay kernel runs after this one)
     int P, L, Lp, V, O, depth_budget, rows_have_sizes;
@@ -663,8 +664,16 @@ __global__ void __launch_bounds__(256, 6) lower_kernel(LowerArgs g) {
     for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
         // rows_have_sizes == 0 (host path uploads one length per tree): sizes are recomputed from the arities
         const int16_t *srow = g.rows_have_sizes ? g.size + (size_t)n * g.L : nullptr;
-        const int len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
-        lower_tree<MULTI, SPLIT>(ln, g.value + (size_t)n * g.L, g.type + (size_t)n * g.L, srow, len, g.L, g.Lp, g.V, g.O,
+        size_t at = (size_t)n * g.L;
+        int len;
+        if (g.offsets) {          // the host path's compact upload (host_api.cu): no size rows, no row padding
+            const unsigned o0 = __ldg(g.offsets + n);
+            at = o0;
+            len = (int)(__ldg(g.offsets + n + 1) - o0);
+        } else {
+            len = g.rows_have_sizes ? (int)__ldg(srow) : (int)__ldg(g.size + n);
+        }
+        lower_tree<MULTI, SPLIT>(ln, g.value + at, g.type + at, srow, len, g.L, g.Lp, g.V, g.O,
                           g.depth_budget, g.prog + (size_t)n * g.Lp, k, g.rows_have_sizes != 0, g.deep_from, g.fold != 0);
         __syncwarp();
     }
