@@ -11,6 +11,7 @@
 //     c + 1, the H2D copy of chunk c + 1 and lowering + replay of chunk c overlap.
 // Staging buffers and worker threads are created once and cached across calls.
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -43,12 +44,15 @@ public:
         for (auto &t : threads_) t.join();
     }
     int size() const { return n_; }
-    void run(const std::function<void(int, int)> &f) {
-        std::unique_lock<std::mutex> lk(mu_);
+    void start(const std::function<void(int, int)> &f) {      // f must stay alive until wait() returns
+        std::lock_guard<std::mutex> lk(mu_);
         job_ = &f;
         pending_ = n_;
         ++generation_;
         cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
         done_.wait(lk, [this] { return pending_ == 0; });
         job_ = nullptr;
     }
@@ -85,10 +89,13 @@ private:
 struct Staging {
     int device = -1;
     size_t chunk_rows = 0, L = 0;
-    // pinned host staging (packed prefixes of one chunk) and their device images, double-buffered
-    float *h_value[2] = {nullptr, nullptr};
-    int16_t *h_type[2] = {nullptr, nullptr};
-    unsigned *h_off[2] = {nullptr, nullptr};
+    // pinned host staging: the packed prefixes of the WHOLE population (chunk after chunk) and per-chunk offsets;
+    // device images of one chunk, double-buffered
+    size_t pop_cap = 0;
+    float *h_value = nullptr;
+    int16_t *h_type = nullptr;
+    unsigned *h_off = nullptr;       // per chunk: nr + 1 offsets relative to the chunk's first node
+    uint16_t *h_len = nullptr;
     float *value[2] = {nullptr, nullptr};
     int16_t *type[2] = {nullptr, nullptr};
     unsigned *off[2] = {nullptr, nullptr};
@@ -98,7 +105,7 @@ struct Staging {
     float *X = nullptr, *labels = nullptr;
     size_t x_cap = 0, lab_cap = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
-    cudaEvent_t data_ready = nullptr, uploaded[2] = {nullptr, nullptr};
+    cudaEvent_t data_ready = nullptr;
     WorkerPool *pool = nullptr;
 };
 Staging g_st;
@@ -107,14 +114,14 @@ std::mutex g_mu;
 void release_locked() {
     if (g_st.device >= 0) {
         cudaSetDevice(g_st.device);
+        if (g_st.h_value) cudaFreeHost(g_st.h_value);
+        if (g_st.h_type) cudaFreeHost(g_st.h_type);
+        if (g_st.h_off) cudaFreeHost(g_st.h_off);
+        free(g_st.h_len);
         for (int i = 0; i < 2; ++i) {
-            if (g_st.h_value[i]) cudaFreeHost(g_st.h_value[i]);
-            if (g_st.h_type[i]) cudaFreeHost(g_st.h_type[i]);
-            if (g_st.h_off[i]) cudaFreeHost(g_st.h_off[i]);
             cudaFree(g_st.value[i]); cudaFree(g_st.type[i]); cudaFree(g_st.off[i]);
             cudaFree(g_st.ws[i]); cudaFree(g_st.fitness[i]);
             if (g_st.stream[i]) cudaStreamDestroy(g_st.stream[i]);
-            if (g_st.uploaded[i]) cudaEventDestroy(g_st.uploaded[i]);
         }
         cudaFree(g_st.X); cudaFree(g_st.labels);
         if (g_st.data_ready) cudaEventDestroy(g_st.data_ready);
@@ -123,8 +130,8 @@ void release_locked() {
     g_st = Staging();
 }
 
-int prepare(int device, size_t rows, size_t L, size_t xbytes, size_t lbytes) {
-    if (g_st.device != device || g_st.chunk_rows < rows || g_st.L != L) {
+int prepare(int device, size_t pop, size_t rows, size_t L, size_t xbytes, size_t lbytes) {
+    if (g_st.device != device || g_st.chunk_rows < rows || g_st.L != L || g_st.pop_cap < pop) {
         WorkerPool *pool = g_st.pool;      // threads survive a re-size of the buffers
         g_st.pool = nullptr;
         release_locked();
@@ -134,17 +141,19 @@ int prepare(int device, size_t rows, size_t L, size_t xbytes, size_t lbytes) {
         g_st.chunk_rows = rows;
         g_st.L = L;
         g_st.ws_bytes = evogp_eval_workspace_bytes((unsigned)rows, (unsigned)L);
+        g_st.pop_cap = pop;
+        const size_t chunks = (pop + rows - 1) / rows;
+        EVOGP_CUDA(cudaHostAlloc(&g_st.h_value, pop * L * sizeof(float), cudaHostAllocDefault));
+        EVOGP_CUDA(cudaHostAlloc(&g_st.h_type, pop * L * sizeof(int16_t), cudaHostAllocDefault));
+        EVOGP_CUDA(cudaHostAlloc(&g_st.h_off, (pop + chunks) * sizeof(unsigned), cudaHostAllocDefault));
+        g_st.h_len = static_cast<uint16_t *>(malloc(pop * sizeof(uint16_t)));
         for (int i = 0; i < 2; ++i) {
-            EVOGP_CUDA(cudaHostAlloc(&g_st.h_value[i], rows * L * sizeof(float), cudaHostAllocDefault));
-            EVOGP_CUDA(cudaHostAlloc(&g_st.h_type[i], rows * L * sizeof(int16_t), cudaHostAllocDefault));
-            EVOGP_CUDA(cudaHostAlloc(&g_st.h_off[i], (rows + 1) * sizeof(unsigned), cudaHostAllocDefault));
             EVOGP_CUDA(cudaMalloc(&g_st.value[i], rows * L * sizeof(float)));
             EVOGP_CUDA(cudaMalloc(&g_st.type[i], rows * L * sizeof(int16_t)));
             EVOGP_CUDA(cudaMalloc(&g_st.off[i], (rows + 1) * sizeof(unsigned)));
             EVOGP_CUDA(cudaMalloc(&g_st.ws[i], g_st.ws_bytes));
             EVOGP_CUDA(cudaMalloc(&g_st.fitness[i], rows * sizeof(float)));
             EVOGP_CUDA(cudaStreamCreateWithFlags(&g_st.stream[i], cudaStreamNonBlocking));
-            EVOGP_CUDA(cudaEventCreateWithFlags(&g_st.uploaded[i], cudaEventDisableTiming));
         }
         EVOGP_CUDA(cudaEventCreateWithFlags(&g_st.data_ready, cudaEventDisableTiming));
     }
@@ -193,7 +202,7 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     if (rows > 65536) rows = 65536;
     const size_t L = gpLen;
     const size_t xbytes = (size_t)dataPoints * varLen * sizeof(float), lbytes = (size_t)dataPoints * outLen * sizeof(float);
-    int rc = prepare(device, rows, L, xbytes, lbytes);
+    int rc = prepare(device, popSize, rows, L, xbytes, lbytes);
     if (rc) return rc;
     EVOGP_CUDA(cudaSetDevice(device));
     Staging &s = g_st;
@@ -201,43 +210,77 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     EVOGP_CUDA(cudaMemcpyAsync(s.labels, labels, lbytes, cudaMemcpyHostToDevice, s.stream[0]));
     EVOGP_CUDA(cudaEventRecord(s.data_ready, s.stream[0]));
     EVOGP_CUDA(cudaStreamWaitEvent(s.stream[1], s.data_ready, 0));
-    int c = 0;
-    for (size_t r0 = 0; r0 < popSize; r0 += rows, ++c) {
-        const int b = c & 1;
-        const size_t nr = (popSize - r0 < rows) ? popSize - r0 : rows;
-        cudaStream_t st = s.stream[b];
-        if (c >= 2) EVOGP_CUDA(cudaEventSynchronize(s.uploaded[b]));      // the copies out of this staging pair are done
-        // ---- pack: offsets (serial, one column read per tree), then the prefixes in parallel ----
-        unsigned *off = s.h_off[b];
+    const size_t chunks = (popSize + rows - 1) / rows;
+    WorkerPool &pool = *s.pool;
+    // ---- 1. lengths: the only column of subtree_size the evaluator needs (one cache line per tree: spread over the pool) ----
+    uint16_t *len = s.h_len;
+    const std::function<void(int, int)> lens_job = [&](int w, int nw) {
+        const size_t lo = (size_t)popSize * w / nw, hi = (size_t)popSize * (w + 1) / nw;
+        for (size_t r = lo; r < hi; ++r) {
+            const int v = subtree_size[r * L];
+            len[r] = (uint16_t)(v < 0 ? 0 : (v > (int)L ? (int)L : v));   // impossible lengths become empty rows (-> NaN fitness)
+        }
+    };
+    pool.start(lens_job);
+    pool.wait();
+    // ---- 2. offsets per chunk (relative to the chunk's first node) and the chunk's place in the staging buffers ----
+    std::vector<size_t> node0(chunks + 1, 0);
+    for (size_t c = 0, r0 = 0; c < chunks; ++c, r0 += rows) {
+        const size_t nr = std::min(rows, (size_t)popSize - r0);
+        unsigned *off = s.h_off + r0 + c;
         unsigned total = 0;
         for (size_t r = 0; r < nr; ++r) {
-            int len = subtree_size[(r0 + r) * L];                          // the only column of subtree_size the evaluator needs
-            len = len < 0 ? 0 : (len > (int)L ? (int)L : len);            // impossible lengths become empty rows (-> NaN fitness)
             off[r] = total;
-            total += (unsigned)len;
+            total += len[r0 + r];
         }
         off[nr] = total;
-        float *hv = s.h_value[b];
-        int16_t *ht = s.h_type[b];
-        const std::function<void(int, int)> job = [&](int w, int nw) {
+        node0[c + 1] = node0[c] + total;
+    }
+    // ---- 3. pack chunk after chunk on the pool; this thread enqueues each chunk as soon as it is packed ----
+    std::vector<std::atomic<int>> packed(chunks);
+    for (auto &p : packed) p.store(0, std::memory_order_relaxed);
+    const std::function<void(int, int)> pack_job = [&](int w, int nw) {
+        for (size_t c = 0, r0 = 0; c < chunks; ++c, r0 += rows) {
+            const size_t nr = std::min(rows, (size_t)popSize - r0);
+            const unsigned *off = s.h_off + r0 + c;
+            float *hv = s.h_value + node0[c];
+            int16_t *ht = s.h_type + node0[c];
             const size_t lo = nr * (size_t)w / nw, hi = nr * (size_t)(w + 1) / nw;
             for (size_t r = lo; r < hi; ++r) {
-                const unsigned len = off[r + 1] - off[r];
-                std::memcpy(hv + off[r], value + (r0 + r) * L, len * sizeof(float));
-                std::memcpy(ht + off[r], type + (r0 + r) * L, len * sizeof(int16_t));
+                const unsigned n = off[r + 1] - off[r];
+                std::memcpy(hv + off[r], value + (r0 + r) * L, n * sizeof(float));
+                std::memcpy(ht + off[r], type + (r0 + r) * L, n * sizeof(int16_t));
             }
-        };
-        s.pool->run(job);
-        // ---- upload, evaluate, download ----
-        EVOGP_CUDA(cudaMemcpyAsync(s.value[b], hv, (size_t)total * sizeof(float), cudaMemcpyHostToDevice, st));
-        EVOGP_CUDA(cudaMemcpyAsync(s.type[b], ht, (size_t)total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        EVOGP_CUDA(cudaMemcpyAsync(s.off[b], off, (nr + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-        EVOGP_CUDA(cudaEventRecord(s.uploaded[b], st));
-        rc = evogp_sr_fitness_packed((unsigned)nr, dataPoints, gpLen, varLen, outLen, useMSE, s.value[b], s.type[b], s.off[b], s.X,
-                                     s.labels, s.fitness[b], s.ws[b], s.ws_bytes, st);
-        if (rc) return rc;
-        EVOGP_CUDA(cudaMemcpyAsync(fitnesses + r0, s.fitness[b], nr * sizeof(float), cudaMemcpyDeviceToHost, st));
+            packed[c].fetch_add(1, std::memory_order_release);
+        }
+    };
+    pool.start(pack_job);
+    const int nw = pool.size();
+    for (size_t c = 0, r0 = 0; c < chunks; ++c, r0 += rows) {
+        const int b = (int)(c & 1);
+        const size_t nr = std::min(rows, (size_t)popSize - r0);
+        cudaStream_t st = s.stream[b];
+        while (packed[c].load(std::memory_order_acquire) < nw) std::this_thread::yield();
+        const size_t total = node0[c + 1] - node0[c];
+        rc = EVOGP_OK;
+        cudaError_t e = cudaMemcpyAsync(s.value[b], s.h_value + node0[c], total * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.type[b], s.h_type + node0[c], total * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.off[b], s.h_off + r0 + c, (nr + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            rc = evogp_sr_fitness_packed((unsigned)nr, dataPoints, gpLen, varLen, outLen, useMSE, s.value[b], s.type[b], s.off[b], s.X,
+                                         s.labels, s.fitness[b], s.ws[b], s.ws_bytes, st);
+        if (e == cudaSuccess && rc == EVOGP_OK)
+            e = cudaMemcpyAsync(fitnesses + r0, s.fitness[b], nr * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess || rc != EVOGP_OK) {
+            pool.wait();                                                   // the job references this frame
+            if (e != cudaSuccess) {
+                set_error("host path: %s", cudaGetErrorString(e));
+                return EVOGP_ERR_CUDA;
+            }
+            return rc;
+        }
     }
+    pool.wait();
     EVOGP_CUDA(cudaStreamSynchronize(s.stream[0]));
     EVOGP_CUDA(cudaStreamSynchronize(s.stream[1]));
     return EVOGP_OK;
