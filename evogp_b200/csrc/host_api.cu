@@ -12,6 +12,7 @@
 // Staging buffers and worker threads are created once and cached across calls.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -212,6 +213,9 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     EVOGP_CUDA(cudaStreamWaitEvent(s.stream[1], s.data_ready, 0));
     const size_t chunks = (popSize + rows - 1) / rows;
     WorkerPool &pool = *s.pool;
+    static const bool trace = getenv("EVOGP_HOST_TRACE") != nullptr;    // phase times on stderr (developer aid)
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     // ---- 1. lengths: the only column of subtree_size the evaluator needs (one cache line per tree: spread over the pool) ----
     uint16_t *len = s.h_len;
     const std::function<void(int, int)> lens_job = [&](int w, int nw) {
@@ -223,6 +227,7 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
     };
     pool.start(lens_job);
     pool.wait();
+    const double t_lens = since(t_begin);
     // ---- 2. offsets per chunk (relative to the chunk's first node) and the chunk's place in the staging buffers ----
     std::vector<size_t> node0(chunks + 1, 0);
     for (size_t c = 0, r0 = 0; c < chunks; ++c, r0 += rows) {
@@ -254,13 +259,17 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
             packed[c].fetch_add(1, std::memory_order_release);
         }
     };
+    const double t_offsets = since(t_begin);
     pool.start(pack_job);
     const int nw = pool.size();
+    double t_first = 0, t_lastpack = 0;
     for (size_t c = 0, r0 = 0; c < chunks; ++c, r0 += rows) {
         const int b = (int)(c & 1);
         const size_t nr = std::min(rows, (size_t)popSize - r0);
         cudaStream_t st = s.stream[b];
         while (packed[c].load(std::memory_order_acquire) < nw) std::this_thread::yield();
+        if (c == 0) t_first = since(t_begin);
+        if (c + 1 == chunks) t_lastpack = since(t_begin);
         const size_t total = node0[c + 1] - node0[c];
         rc = EVOGP_OK;
         cudaError_t e = cudaMemcpyAsync(s.value[b], s.h_value + node0[c], total * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -281,7 +290,11 @@ extern "C" int evogp_SR_fitness_host(unsigned popSize, unsigned dataPoints, unsi
         }
     }
     pool.wait();
+    const double t_enqueued = since(t_begin);
     EVOGP_CUDA(cudaStreamSynchronize(s.stream[0]));
     EVOGP_CUDA(cudaStreamSynchronize(s.stream[1]));
+    if (trace)
+        fprintf(stderr, "[evogp host] lens %.3f  offsets %.3f  first chunk packed %.3f  last chunk packed %.3f  all enqueued %.3f  done %.3f ms (%zu nodes, %d threads)\n",
+                t_lens, t_offsets, t_first, t_lastpack, t_enqueued, since(t_begin), node0[chunks], nw);
     return EVOGP_OK;
 }
