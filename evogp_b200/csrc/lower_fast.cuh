@@ -29,6 +29,12 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
     return x;
 }
 
+// folding anything but + - * / goes out of line: the operator bodies (sinh, pow, ...) are hundreds of instructions that
+// would otherwise sit in the middle of the hot path's instruction stream
+__device__ __noinline__ float fold_rare(unsigned arity, unsigned fid, float x, float y) {
+    return arity == 1u ? fold_unary(unary_slot(fid), x) : fold_binary(binary_slot(fid), x, y);
+}
+
 // per-warp scratch: 4 arrays of NSETS * 32 + 1 words
 template <int NSETS>
 __host__ __device__ constexpr size_t lower_fast_scratch_bytes() { return (size_t)4 * (NSETS * 32 + 1) * 4; }
@@ -123,7 +129,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane, const float *val,
                         const float r0 = binary_op<0>(x, y), r1 = binary_op<1>(x, y), r2 = binary_op<2>(x, y), r3 = binary_op<3>(x, y);
                         r = b == 0u ? r0 : (b == 1u ? r1 : (b == 2u ? r2 : r3));
                     } else {
-                        r = ar[k] == 1u ? fold_unary(unary_slot(fid[k]), x) : fold_binary(binary_slot(fid[k]), x, y);
+                        r = fold_rare(ar[k], fid[k], x, y);
                     }
                     t[k] = NT_CONST; v[k] = __float_as_uint(r); ar[k] = 0u;
                     TS[lane + 32 * k] = (uint32_t)NT_CONST | (s[k] << 16);
