@@ -141,4 +141,105 @@ __device__ inline int grow_tree(Rng &rng, const GrowParams &g, uint32_t *val, ui
     return cnt;
 }
 
+
+// ---------------------------------------------------------------------------
+// Packed, branch-free growth (single-output trees, taus88 draws) - shared by generate_fast_kernel (generate.cu) and the
+// donor phase of nextgen_kernel (nextgen.cu).  Same draws, same trees as grow_tree<false, Taus88>.
+// ---------------------------------------------------------------------------
+struct Taus88State {
+    uint32_t z1, z2, z3;
+};
+__device__ __forceinline__ uint32_t taus88_step(Taus88State &s) {
+    uint32_t b;
+    b = ((s.z1 << 13) ^ s.z1) >> 19;
+    s.z1 = ((s.z1 & 0xFFFFFFFEu) << 12) ^ b;
+    b = ((s.z2 << 2) ^ s.z2) >> 25;
+    s.z2 = ((s.z2 & 0xFFFFFFF8u) << 4) ^ b;
+    b = ((s.z3 << 3) ^ s.z3) >> 11;
+    s.z3 = ((s.z3 & 0xFFFFFFF0u) << 17) ^ b;
+    return s.z1 ^ s.z2 ^ s.z3;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return __uint2float_rn(x) * 2.3283064365386963e-10f; }   // float(u32) / 2^32
+
+// x % d for a divisor known before the loop: Lemire's fastmod, M = floor(2^64 / d) + 1 computed on the host
+__device__ __forceinline__ uint32_t fastmod_u32(uint32_t x, uint64_t M, uint32_t d) {
+    return (uint32_t)__umul64hi(M * x, (uint64_t)d);
+}
+
+
+// Node word: [2:0] type, [15:4] subtree size, [31:16] variable / constant-sample index (leaves); functions keep their
+// id in [20:16] and, while their frame is open, the index of the enclosing function node in [31:21].
+// s_leaf: 16 floats (depth -> leaf probability, 2.0 beyond MAX_FULL_DEPTH); s_roul: 32 floats (cumulative roulette padded
+// with +inf); mono: the roulette is non-decreasing (binary search allowed).  Returns the tree length (0 when !active).
+__device__ __forceinline__ int grow_tree_packed(uint32_t seed, bool active, const float *s_leaf, const float *s_roul, bool mono,
+                                                uint32_t V, uint32_t S, uint64_t MV, uint64_t MS, float constProb, int L,
+                                                uint32_t *row) {
+    int cnt = 0, d = active ? 0 : -1;
+    uint32_t owed = 1;                 // children still owed per depth, 2 bits each (arity <= 3); root frame {1, 0}
+    uint32_t cur = 0;                  // the function node whose children are being generated (depth >= 1)
+    Taus88State st;
+    st.z1 = st.z2 = st.z3 = seed;
+    while (d >= 0 && cnt < L) {
+        owed -= 1u << (2 * d);                                     // cd.childs-- (generate.cu:61)
+        const float leafp = s_leaf[d];
+        // draws: u (leaf test); then r (roulette) or u (constant test) - the same word; then, for a leaf only, a raw word.
+        // All three are made; a function commits the state after two.
+        Taus88State s1 = st;
+        const uint32_t o1 = taus88_step(s1);
+        Taus88State s2 = s1;
+        const uint32_t o2 = taus88_step(s2);
+        Taus88State s3 = s2;
+        const uint32_t o3 = taus88_step(s3);
+        const bool is_func = u32_to_unit(o1) >= leafp;             // :71
+        const float r = u32_to_unit(o2);
+        int k = 0;                                                 // number of roulette entries <= r (:74-84)
+        if (mono) {
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s_roul[k + step - 1] <= r) k += step;
+        } else {
+            for (int i = F_END - 1; i >= 0; --i)
+                if (r >= s_roul[i]) { k = i + 1; break; }
+        }
+        const uint32_t ftype = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
+        const bool is_const = r <= constProb;                      // :109
+        const uint32_t idx = is_const ? fastmod_u32(o3, MS, S) : fastmod_u32(o3, MV, V);
+        st.z1 = is_func ? s2.z1 : s3.z1;
+        st.z2 = is_func ? s2.z2 : s3.z2;
+        st.z3 = is_func ? s2.z3 : s3.z3;
+        if (is_func) {                                             // open the frame of its children
+            row[cnt] = ((uint32_t)k << 16) | (cur << 21) | ftype;
+            cur = (uint32_t)cnt;
+            ++d;
+            owed |= (ftype - 1u) << (2 * d);
+            ++cnt;
+        } else {
+            row[cnt] = (idx << 16) | (1u << 4) | (is_const ? (uint32_t)NT_CONST : (uint32_t)NT_VAR);
+            ++cnt;
+            while (d >= 0 && ((owed >> (2 * d)) & 3u) == 0u) {      // frames whose children are all there: their node is complete
+                if (d > 0) {
+                    const uint32_t w = row[cur];
+                    row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
+                    cur = w >> 21;
+                }
+                --d;
+            }
+        }
+    }
+    for (; d > 0; --d) {   // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open
+        const uint32_t w = row[cur];
+        row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
+        cur = w >> 21;
+    }
+    return cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
+}
+
+// packed node word -> value bits, node type, subtree size
+__device__ __forceinline__ void decode_packed_node(uint32_t w, const float *consts, uint32_t &v, uint32_t &t, uint32_t &sz) {
+    t = w & 7u;
+    sz = (w >> 4) & 0xFFFu;
+    const uint32_t code = w >> 16;
+    v = t == NT_CONST ? __float_as_uint(__ldg(consts + code)) : __float_as_uint((float)(t == NT_VAR ? code : (code & 31u)));
+}
+
 }  // namespace evogp

@@ -123,26 +123,6 @@ using namespace evogp;
 //     2 bits per depth in one 32-bit register; `raw % V` / `raw % S` use precomputed 64-bit reciprocals;
 //   * each warp writes its own 32 rows as soon as its longest tree is done (no CTA barrier).
 // ---------------------------------------------------------------------------
-struct Taus88State {
-    uint32_t z1, z2, z3;
-};
-__device__ __forceinline__ uint32_t taus88_step(Taus88State &s) {
-    uint32_t b;
-    b = ((s.z1 << 13) ^ s.z1) >> 19;
-    s.z1 = ((s.z1 & 0xFFFFFFFEu) << 12) ^ b;
-    b = ((s.z2 << 2) ^ s.z2) >> 25;
-    s.z2 = ((s.z2 & 0xFFFFFFF8u) << 4) ^ b;
-    b = ((s.z3 << 3) ^ s.z3) >> 11;
-    s.z3 = ((s.z3 & 0xFFFFFFF0u) << 17) ^ b;
-    return s.z1 ^ s.z2 ^ s.z3;
-}
-__device__ __forceinline__ float u32_to_unit(uint32_t x) { return __uint2float_rn(x) * 2.3283064365386963e-10f; }   // float(u32) / 2^32
-
-// x % d for a divisor known before the loop: Lemire's fastmod, M = floor(2^64 / d) + 1 computed on the host
-__device__ __forceinline__ uint32_t fastmod_u32(uint32_t x, uint64_t M, uint32_t d) {
-    return (uint32_t)__umul64hi(M * x, (uint64_t)d);
-}
-
 // single-output trees (out_len == 1; multi-output populations keep generate_kernel)
 __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     extern __shared__ uint32_t gsm[];
@@ -167,77 +147,13 @@ __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     const uint64_t MV = g.magicV, MS = g.magicS;
     const float constProb = g.constProb;
 
-    // Node word: [2:0] type, [15:4] subtree size, [31:16] variable / constant-sample index (leaves); functions keep their
-    // id in [20:16] and, while their frame is open, the index of the enclosing function node in [31:21].
-    int cnt = 0, d = n < g.P ? 0 : -1;
-    uint32_t owed = 1;                 // children still owed per depth, 2 bits each (arity <= 3); root frame {1, 0}
-    uint32_t cur = 0;                  // the function node whose children are being generated (depth >= 1)
-    Taus88State st;
-    st.z1 = st.z2 = st.z3 = tree_seed(n, g.keys[0], g.keys[1]);
-    while (d >= 0 && cnt < L) {
-        owed -= 1u << (2 * d);                                     // cd.childs-- (generate.cu:61)
-        const float leafp = s_leaf[d];
-        // draws: u (leaf test); then r (roulette) or u (constant test) - the same word; then, for a leaf only, a raw word.
-        // All three are made; a function commits the state after two.
-        Taus88State s1 = st;
-        const uint32_t o1 = taus88_step(s1);
-        Taus88State s2 = s1;
-        const uint32_t o2 = taus88_step(s2);
-        Taus88State s3 = s2;
-        const uint32_t o3 = taus88_step(s3);
-        const bool is_func = u32_to_unit(o1) >= leafp;             // :71
-        const float r = u32_to_unit(o2);
-        int k = 0;                                                 // number of roulette entries <= r (:74-84)
-        if (mono) {
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (s_roul[k + step - 1] <= r) k += step;
-        } else {
-            for (int i = F_END - 1; i >= 0; --i)
-                if (r >= s_roul[i]) { k = i + 1; break; }
-        }
-        const uint32_t ftype = k <= F_IF ? NT_TFUNC : (k <= F_GE ? NT_BFUNC : NT_UFUNC);
-        const bool is_const = r <= constProb;                      // :109
-        const uint32_t idx = is_const ? fastmod_u32(o3, MS, S) : fastmod_u32(o3, MV, V);
-        st.z1 = is_func ? s2.z1 : s3.z1;
-        st.z2 = is_func ? s2.z2 : s3.z2;
-        st.z3 = is_func ? s2.z3 : s3.z3;
-        if (is_func) {                                             // open the frame of its children
-            row[cnt] = ((uint32_t)k << 16) | (cur << 21) | ftype;
-            cur = (uint32_t)cnt;
-            ++d;
-            owed |= (ftype - 1u) << (2 * d);
-            ++cnt;
-        } else {
-            row[cnt] = (idx << 16) | (1u << 4) | (is_const ? (uint32_t)NT_CONST : (uint32_t)NT_VAR);
-            ++cnt;
-            while (d >= 0 && ((owed >> (2 * d)) & 3u) == 0u) {      // frames whose children are all there: their node is complete
-                if (d > 0) {
-                    const uint32_t w = row[cur];
-                    row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
-                    cur = w >> 21;
-                }
-                --d;
-            }
-        }
-    }
-    for (; d > 0; --d) {   // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open
-        const uint32_t w = row[cur];
-        row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
-        cur = w >> 21;
-    }
-    const int len = cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
+    const int len = grow_tree_packed(tree_seed(n, g.keys[0], g.keys[1]), n < g.P, s_leaf, s_roul, mono, V, S, MV, MS, constProb, L, row);
     __syncwarp();
 
     // ---- this warp's 32 rows leave through coalesced, zero-filled stores ----
     const unsigned first = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
     const uint32_t *rows = gsm + (size_t)(threadIdx.x & ~31) * pitch;
-    auto decode = [&](uint32_t w, uint32_t &v, uint32_t &t, uint32_t &sz) {
-        t = w & 7u;
-        sz = (w >> 4) & 0xFFFu;
-        const uint32_t code = w >> 16;
-        v = t == NT_CONST ? __float_as_uint(__ldg(g.consts + code)) : __float_as_uint((float)(t == NT_VAR ? code : (code & 31u)));
-    };
+    auto decode = [&](uint32_t w, uint32_t &v, uint32_t &t, uint32_t &sz) { decode_packed_node(w, g.consts, v, t, sz); };
     for (int r = 0; r < 32; ++r) {
         const unsigned tree = first + r;
         if (tree >= g.P) break;

@@ -16,6 +16,7 @@
 // cannot be reproduced inside a kernel), so this path is statistically — not bit-for-bit —
 // equivalent to DefaultSelection/DefaultCrossover/DefaultMutation.  It is deterministic in
 // (keys, inputs), which is what replicated multi-GPU populations need.
+#include <cstdlib>
 #include "gen_tree.cuh"
 
 namespace evogp {
@@ -152,6 +153,124 @@ __global__ void __launch_bounds__(256) nextgen_kernel(NextGenArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// nextgen_batch_kernel — single-output populations.  nextgen_kernel above grows the donor of a mutation on lane 0 while
+// 31 lanes wait: with mutation_rate 0.2 that serial growth is 420 of the 579 warp-instructions a child costs
+// (profiles/r2_genetic_ncu.txt).  Here a warp takes 32 children at a time: first every lane decides its own child's
+// mutation coin and grows that child's donor (grow_tree_packed: branch-free, 32 donors at once), then the warp splices
+// the 32 children one after the other exactly as before.  Same draws, same children (oracle_next_generation).
+// ---------------------------------------------------------------------------
+struct NextGenBatchArgs {
+    NextGenArgs a;
+    unsigned long long magicV, magicS;
+    int pitch;     // words per donor row (odd)
+};
+
+__global__ void __launch_bounds__(256) nextgen_batch_kernel(NextGenBatchArgs gb) {
+    const NextGenArgs &g = gb.a;
+    extern __shared__ __align__(16) uint32_t ng_smem[];
+    __shared__ float s_leaf[16];
+    __shared__ float s_roul[32];
+    __shared__ int s_mono;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int L = g.L, pitch = gb.pitch;
+    if (threadIdx.x < 16) s_leaf[threadIdx.x] = threadIdx.x < kMaxFullDepth ? g.depth2leaf[threadIdx.x] : 2.0f;
+    if (threadIdx.x < 32) s_roul[threadIdx.x] = threadIdx.x < F_END ? g.roulette[threadIdx.x] : __int_as_float(0x7f800000);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mono = 1;
+        for (int i = 1; i < F_END; ++i) mono &= s_roul[i] >= s_roul[i - 1];
+        s_mono = mono;
+    }
+    __syncthreads();
+    const bool mono = s_mono != 0;
+    // per warp: child row (value bits, type | size << 16): 2 L words; then 32 donor rows of `pitch` packed words
+    uint32_t *cv = ng_smem + (size_t)warp * (2 * L + 32 * pitch), *cts = cv + L, *donors = cts + L;
+    uint32_t *my_donor = donors + (size_t)lane * pitch;
+    const uint32_t k0 = g.keys[0], k1 = g.keys[1];
+    const int nbatch = (g.P + 31) / 32;
+
+    for (int batch = blockIdx.x * nwarp + warp; batch < nbatch; batch += gridDim.x * nwarp) {
+        // ---- phase A: lane i looks after child batch * 32 + i: mutation coin, donor ----
+        const int mine = batch * 32 + lane;
+        const bool child = mine >= g.elite && mine < g.P;
+        const uint4 q1 = philox_block((uint32_t)mine, 1u, k0, k1);
+        const bool mutate = child && __uint2float_rn(q1.x) * 2.3283064365386963e-10f < g.mutationRate;
+        const int my_dlen = grow_tree_packed(tree_seed((uint32_t)mine, k0 ^ 0x5bd1e995u, k1), mutate, s_leaf, s_roul, mono, g.V, g.S,
+                                             gb.magicV, gb.magicS, g.constProb, L, my_donor);
+        __syncwarp();
+        // ---- phase B: the warp builds the 32 children one after the other ----
+        for (int i = 0; i < 32; ++i) {
+            const int n = batch * 32 + i;
+            if (n >= g.P) break;
+            float *ov = g.ovalue + (size_t)n * L;
+            int16_t *ot = g.otype + (size_t)n * L;
+            int16_t *os = g.osize + (size_t)n * L;
+            if (n < g.elite) {   // elitism: verbatim copy of the n-th best row
+                const size_t src = (size_t)g.order[n] * L;
+                for (int j = lane; j < L; j += 32) {
+                    ov[j] = g.value[src + j];
+                    ot[j] = g.type[src + j];
+                    os[j] = g.size[src + j];
+                }
+                continue;
+            }
+            const uint4 r0 = philox_block((uint32_t)n, 0u, k0, k1);
+            const uint32_t mut_word = __shfl_sync(0xffffffffu, q1.y, i);
+            const int dlen = __shfl_sync(0xffffffffu, mutate ? my_dlen : -1, i);      // -1: no mutation for this child
+            const size_t lrow = (size_t)g.order[r0.x % (uint32_t)g.survivors] * L;
+            const size_t rrow = (size_t)g.order[r0.y % (uint32_t)g.survivors] * L;
+            const int llen = g.size[lrow], rlen = g.size[rrow];
+            const int lpos = (int)(r0.z % (uint32_t)max(llen, 1)), rpos = (int)(r0.w % (uint32_t)max(rlen, 1));
+            const bool rows_ok = llen >= 1 && llen <= L && rlen >= 1 && rlen <= L;
+            const SplicePlan cx = plan_splice(llen, lpos, rows_ok ? g.size[lrow + lpos] : 0, rpos,
+                                              rows_ok ? g.size[rrow + rpos] : 0, L, rows_ok);
+            for (int j = lane; j < L; j += 32) {       // crossover into shared memory
+                uint32_t v = 0, ts = 0;
+                if (j < cx.newlen) {
+                    size_t q;
+                    int add = 0;
+                    if (j < cx.pos) {
+                        q = lrow + j;
+                        if (j + g.size[q] > cx.pos) add = cx.diff;     // ancestor of the splice point
+                    } else if (j < cx.pos + cx.dsub) q = rrow + cx.dpos + j - cx.pos;
+                    else q = lrow + j - cx.diff;
+                    v = __float_as_uint(g.value[q]);
+                    ts = ((uint32_t)(uint16_t)g.type[q]) | ((uint32_t)(uint16_t)(g.size[q] + add) << 16);
+                }
+                cv[j] = v;
+                cts[j] = ts;
+            }
+            __syncwarp();
+            SplicePlan mu = plan_splice(cx.newlen, cx.newlen, 0, 0, 0, L, false);      // identity
+            if (dlen >= 0) {
+                const int mpos = (int)(mut_word % (uint32_t)max(cx.newlen, 1));
+                mu = plan_splice(cx.newlen, mpos, (int)(cts[mpos] >> 16), 0, dlen, L, dlen >= 1);
+            }
+            const uint32_t *drow = donors + (size_t)i * pitch;
+            for (int j = lane; j < L; j += 32) {       // child (or mutated child) -> global, zero-filled tail
+                uint32_t v = 0, t = 0, sz = 0;
+                if (j < mu.newlen) {
+                    if (j < mu.pos) {
+                        v = cv[j]; t = cts[j] & 0xFFFFu; sz = cts[j] >> 16;
+                        if (j + (int)sz > mu.pos) sz += mu.diff;
+                    } else if (j < mu.pos + mu.dsub) {
+                        decode_packed_node(drow[j - mu.pos], g.consts, v, t, sz);
+                    } else {
+                        const int q = j - mu.diff;
+                        v = cv[q]; t = cts[q] & 0xFFFFu; sz = cts[q] >> 16;
+                    }
+                }
+                ov[j] = __uint_as_float(v);
+                ot[j] = (int16_t)t;
+                os[j] = (int16_t)sz;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace evogp
 
 using namespace evogp;
@@ -178,17 +297,38 @@ extern "C" int evogp_next_generation(int popSize, int gpLen, const float *value,
     a.P = popSize; a.L = gpLen; a.elite = eliteCnt; a.survivors = survivorCnt;
     a.V = varLen; a.O = outLen; a.S = constSamplesLen;
     a.mutationRate = mutationRate; a.outProb = outProb; a.constProb = constProb;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool use_batch = []() { const char *e = getenv("EVOGP_NEXTGEN_BATCH"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (use_batch && outLen == 1 && varLen <= 65535 && constSamplesLen <= 65535) {
+        NextGenBatchArgs gb;
+        gb.a = a;
+        gb.magicV = ~0ull / varLen + 1ull;
+        gb.magicS = ~0ull / constSamplesLen + 1ull;
+        gb.pitch = gpLen | 1;
+        const size_t per_warp = ((size_t)2 * gpLen + (size_t)32 * gb.pitch) * 4;
+        int warps = 8;
+        while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;      // three CTAs per SM at max_tree_len 64
+        const size_t smem = warps * per_warp;
+        if (smem <= 200 * 1024) {
+            if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(nextgen_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            long long grid = (((long long)popSize + 31) / 32 + warps - 1) / warps;
+            const long long cap = (long long)sms * 3;
+            if (grid > cap) grid = cap;
+            nextgen_batch_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(gb);
+            count_launch();
+            return check_launch("next_generation");
+        }
+    }
     const size_t per_warp = (size_t)gpLen * 16;
     int warps = 8;
     while (warps > 1 && warps * per_warp > 160 * 1024) warps >>= 1;
     const size_t smem = warps * per_warp;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = ((long long)popSize + warps - 1) / warps;
     const long long cap = (long long)sms * 8;
     if (grid > cap) grid = cap;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (outLen > 1) {
         if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(nextgen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nextgen_kernel<true><<<(unsigned)grid, warps * 32, smem, st>>>(a);
