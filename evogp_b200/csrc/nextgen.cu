@@ -191,10 +191,30 @@ __global__ void __launch_bounds__(256) nextgen_batch_kernel(NextGenBatchArgs gb)
     const int nbatch = (g.P + 31) / 32;
 
     for (int batch = blockIdx.x * nwarp + warp; batch < nbatch; batch += gridDim.x * nwarp) {
-        // ---- phase A: lane i looks after child batch * 32 + i: mutation coin, donor ----
+        // ---- phase A: lane i looks after child batch * 32 + i: all its draws, its parents' header (the chain of dependent
+        //      loads order -> length -> subtree size runs ONCE per batch, 32 children wide, instead of once per child),
+        //      its mutation coin and its donor ----
         const int mine = batch * 32 + lane;
         const bool child = mine >= g.elite && mine < g.P;
-        const uint4 q1 = philox_block((uint32_t)mine, 1u, k0, k1);
+        const uint4 q0 = philox_block((uint32_t)mine, 0u, k0, k1), q1 = philox_block((uint32_t)mine, 1u, k0, k1);
+        long long my_l = 0, my_r = 0;         // parents' rows (elites: the row to copy)
+        int my_llen = 0, my_rlen = 0, my_lpos = 0, my_rpos = 0, my_lsub = 0, my_rsub = 0;
+        if (mine < g.P) {
+            if (child) {
+                my_l = g.order[q0.x % (uint32_t)g.survivors];
+                my_r = g.order[q0.y % (uint32_t)g.survivors];
+                my_llen = g.size[(size_t)my_l * L];
+                my_rlen = g.size[(size_t)my_r * L];
+                my_lpos = (int)(q0.z % (uint32_t)max(my_llen, 1));
+                my_rpos = (int)(q0.w % (uint32_t)max(my_rlen, 1));
+                if (my_llen >= 1 && my_llen <= L && my_rlen >= 1 && my_rlen <= L) {
+                    my_lsub = g.size[(size_t)my_l * L + my_lpos];
+                    my_rsub = g.size[(size_t)my_r * L + my_rpos];
+                }
+            } else {
+                my_l = g.order[mine];
+            }
+        }
         const bool mutate = child && __uint2float_rn(q1.x) * 2.3283064365386963e-10f < g.mutationRate;
         const int my_dlen = grow_tree_packed(tree_seed((uint32_t)mine, k0 ^ 0x5bd1e995u, k1), mutate, s_leaf, s_roul, mono, g.V, g.S,
                                              gb.magicV, gb.magicS, g.constProb, L, my_donor);
@@ -206,25 +226,23 @@ __global__ void __launch_bounds__(256) nextgen_batch_kernel(NextGenBatchArgs gb)
             float *ov = g.ovalue + (size_t)n * L;
             int16_t *ot = g.otype + (size_t)n * L;
             int16_t *os = g.osize + (size_t)n * L;
+            const size_t lrow = (size_t)__shfl_sync(0xffffffffu, my_l, i) * L;
             if (n < g.elite) {   // elitism: verbatim copy of the n-th best row
-                const size_t src = (size_t)g.order[n] * L;
                 for (int j = lane; j < L; j += 32) {
-                    ov[j] = g.value[src + j];
-                    ot[j] = g.type[src + j];
-                    os[j] = g.size[src + j];
+                    ov[j] = g.value[lrow + j];
+                    ot[j] = g.type[lrow + j];
+                    os[j] = g.size[lrow + j];
                 }
                 continue;
             }
-            const uint4 r0 = philox_block((uint32_t)n, 0u, k0, k1);
+            const size_t rrow = (size_t)__shfl_sync(0xffffffffu, my_r, i) * L;
+            const int llen = __shfl_sync(0xffffffffu, my_llen, i), rlen = __shfl_sync(0xffffffffu, my_rlen, i);
+            const int lpos = __shfl_sync(0xffffffffu, my_lpos, i), rpos = __shfl_sync(0xffffffffu, my_rpos, i);
+            const int lsub = __shfl_sync(0xffffffffu, my_lsub, i), rsub = __shfl_sync(0xffffffffu, my_rsub, i);
             const uint32_t mut_word = __shfl_sync(0xffffffffu, q1.y, i);
             const int dlen = __shfl_sync(0xffffffffu, mutate ? my_dlen : -1, i);      // -1: no mutation for this child
-            const size_t lrow = (size_t)g.order[r0.x % (uint32_t)g.survivors] * L;
-            const size_t rrow = (size_t)g.order[r0.y % (uint32_t)g.survivors] * L;
-            const int llen = g.size[lrow], rlen = g.size[rrow];
-            const int lpos = (int)(r0.z % (uint32_t)max(llen, 1)), rpos = (int)(r0.w % (uint32_t)max(rlen, 1));
             const bool rows_ok = llen >= 1 && llen <= L && rlen >= 1 && rlen <= L;
-            const SplicePlan cx = plan_splice(llen, lpos, rows_ok ? g.size[lrow + lpos] : 0, rpos,
-                                              rows_ok ? g.size[rrow + rpos] : 0, L, rows_ok);
+            const SplicePlan cx = plan_splice(llen, lpos, lsub, rpos, rsub, L, rows_ok);
             for (int j = lane; j < L; j += 32) {       // crossover into shared memory
                 uint32_t v = 0, ts = 0;
                 if (j < cx.newlen) {
