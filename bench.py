@@ -81,8 +81,9 @@ def measured_peak():
 
 
 def ncu_facts(cfg_id):
-    """DRAM traffic / issue-slot utilisation of the dominant kernel, from the committed ncu capture of this workload
-    (profiles/r2_ncu_facts.json, written by profiles/summarize_ncu.py from the .ncu-rep) — null when there is none."""
+    """DRAM traffic (per tree: it is the program rows the kernel streams) and issue-slot utilisation of the dominant
+    kernel, from the committed ncu capture of this workload (profiles/r2_ncu_facts.json <- profiles/r2_eval_config*_ncu.txt)
+    — null when there is none."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_ncu_facts.json")) as f:
             return json.load(f).get("config%d" % cfg_id)
@@ -701,7 +702,7 @@ def run_ours(args, out):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "replay_kernel", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak,
-                             "traffic": facts.get("replay_dram_bytes_per_launch"),
+                             "traffic": (facts["replay_dram_bytes_per_tree"] * (hi - lo)) if "replay_dram_bytes_per_tree" in facts else None,
                              "traffic_source": facts.get("source"),
                              "algorithmic_bytes": algorithmic_bytes(hi - lo, L, N, V, O), "peak_source": peak_src,
                              "kernel_ms": kms, "kernel_share_of_step": kms / ms_step,
