@@ -75,7 +75,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"multi-gpu check ok on {world} ranks: sharded fitness bit-identical, populations identical for 3 generations; "
-              f"fitness exchange fused into the kernel: {fused} {why}")
+              f"fitness exchange over peer-mapped memory: {fused} ({getattr(sharded._exchange, 'mode', '-')}) {why}")
     dist.destroy_process_group()
 
 
