@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times every BASELINE.json config on ONE B200 (configs 3 and 5 also as the per-GPU shard of the 8-GPU layout)
-and prints a JSON report (kept as profiles/r1_configs.json).  CUDA-event timed, median of several repetitions."""
+and prints a JSON report (kept as profiles/r2_configs.json).  CUDA-event timed, median of several repetitions."""
 import json
 import os
 import sys
@@ -83,6 +83,17 @@ def main():
            "transcendental_mean_tree_len": float(ft.batch_subtree_size[:, 0].float().mean())}
     if ref:
         var["transcendental_reference_cuda_ms"] = ref_time(lambda: ref.sr_fitness(ft.batch_node_value, ft.batch_node_type, ft.batch_subtree_size, X, y))
+    # every function of the reference (if / pow / sinh / cosh leave the PTX fast path for the generic interpreter)
+    ALL = ["if", "+", "-", "*", "/", "loose_div", "pow", "loose_pow", "max", "min", "<", ">", "<=", ">=", "sin", "cos", "tan", "sinh", "cosh",
+           "tanh", "log", "loose_log", "exp", "inv", "loose_inv", "neg", "abs", "sqrt", "loose_sqrt"]
+    da = GenerateDescriptor(max_tree_len=64, input_len=3, output_len=1, using_funcs=ALL, max_layer_cnt=4, const_samples=[-1, 0, 1])
+    fa = Forest.random_generate(100000, da)
+    ms_a = ev_time(lambda: fa.SR_fitness(X, y))
+    var.update({"all_29_funcs_ms": ms_a, "all_29_funcs_tree_evals_per_s": 1e5 * 1024 / ms_a * 1e3,
+                "all_29_funcs_mean_tree_len": float(fa.batch_subtree_size[:, 0].float().mean())})
+    if ref:
+        var["all_29_funcs_reference_cuda_ms"] = ref_time(lambda: ref.sr_fitness(fa.batch_node_value, fa.batch_node_type, fa.batch_subtree_size, X, y))
+    del fa
     prob2 = SymbolicRegression(datapoints=X, labels=y)
     algo2 = GeneticProgramming(f, DefaultCrossover(), DefaultMutation(0.2, d.update(max_layer_cnt=3)), DefaultSelection(0.3, elite_rate=0.01))
     for _ in range(20):
@@ -118,9 +129,11 @@ def main():
     onehot = torch.nn.functional.one_hot(labels.long(), 3).float().contiguous()
     ms_fit = ev_time(lambda: f.SR_fitness(Xc, onehot), reps=5)
     cls = Classification(datapoints=Xc, labels=labels, multi_output=True)
-    ms_cls = ev_time(lambda: cls.evaluate(f), reps=3, warm=1)
+    ms_cls = ev_time(lambda: cls.evaluate(f), reps=5, warm=2)
+    ms_unf = ev_time(lambda: cls.evaluate_unfused(f), reps=2, warm=1)
     rep["config4_pop2e5_L128_N4096_V13_O3"] = {"sr_fitness_onehot_ms": ms_fit, "tree_evals_per_s": 2e5 * 4096 / ms_fit * 1e3,
-                                              "classification_accuracy_ms (fused batch_forward 9.8 GB + softmax/argmax in torch)": ms_cls,
+                                              "classification_accuracy_fused_ms": ms_cls, "classification_tree_evals_per_s": 2e5 * 4096 / ms_cls * 1e3,
+                                              "classification_accuracy_unfused_ms (batch_forward 9.8 GB + softmax/argmax in torch)": ms_unf,
                                               "datapoint_tiles": "16 x 4096 floats > staging area: tiled launches"}
     del f
     torch.cuda.empty_cache()
