@@ -383,3 +383,23 @@ def test_pareto_front_matches_the_reference_formulation(api, orc):
         for got, want in zip((pf.solution.batch_node_value, pf.solution.batch_node_type, pf.solution.batch_subtree_size), ref_sol):
             assert torch.equal(got[have], want[have])
     assert torch.isfinite(pf.fitness).sum() > 5
+
+
+def test_transformation_correlation_fitness(api, orc):
+    """|corr(output, label)| as the reference computes it (transformation.py:36-43), on the fused batch_forward."""
+    tree, _, problem, _ = api
+    P, L, V, N = 800, 32, 4, 200
+    v, t, s = make_forest(orc, P, L, V, 1, ["+", "-", "*", "neg", "abs", "max"], 4, keys=(71, 72))
+    X, _ = make_data(N, V, seed=13)
+    y = (X[:, 0] * 2 - X[:, 1] + 0.1).astype(np.float32)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    prob = problem.Transformation(datapoints=dX, labels=dy)
+    got = prob.evaluate(tree.Forest(V, 1, dv, dt, ds)).cpu().numpy()
+    out = torch.from_numpy(orc.batch_forward(v, t, s, X, 1, nthreads=8)).squeeze(-1)        # exact ops: bit-comparable
+    oc, lc = out - out.mean(), torch.from_numpy(y) - torch.from_numpy(y).mean()
+    want = torch.abs((oc * lc).sum(1) / torch.sqrt((oc ** 2).sum(1) * (lc ** 2).sum())).numpy()
+    both = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got[both], want[both], rtol=2e-4, atol=2e-6)
+    feats = prob.new_feature(tree.Forest(V, 1, dv, dt, ds), n_best=20, n_features=5)
+    assert feats.shape == (N, 5)
