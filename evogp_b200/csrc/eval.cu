@@ -124,15 +124,12 @@ static int launch_lower_t(const Workspace &w, unsigned P, unsigned L, unsigned V
 static const bool g_lower_fast = []() { const char *e = getenv("EVOGP_LOWER_FAST"); return !(e && e[0] == '0'); }();
 
 // the register-resident pass of lower_fast.cuh: single-output, max_tree_len <= 64, packed size rows
-// EVOGP_LOWER_LPT=32 keeps one tree per warp in the fast lowering pass (the A/B switch; default 16 = two trees per warp)
-static const int g_lower_lpt = []() { const char *e = getenv("EVOGP_LOWER_LPT"); return (e && atoi(e) == 32) ? 32 : 16; }();
-
-template <int NSETS, int LPT>
+template <int NSETS>
 static int launch_lower_fast(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
                              const int16_t *type, const int16_t *size, int depth, int deep_from, cudaStream_t st) {
-    auto kern = lower_fast_kernel<NSETS, LPT>;
+    auto kern = lower_fast_kernel<NSETS>;
     const int warps = 8;
-    const size_t smem = warps * lower_fast_per_warp<NSETS, LPT>((int)L);
+    const size_t smem = warps * lower_fast_per_warp<NSETS>((int)L);
     LowerArgs a;
     a.value = value; a.type = type; a.size = size;
     a.prog = w.prog; a.sched = w.sched;
@@ -143,27 +140,18 @@ static int launch_lower_fast(const Workspace &w, unsigned P, unsigned L, unsigne
     a.fold = g_fold ? 1 : 0;
     a.chunk_done = w.chunk_done; a.nchunks = (int)chunk_words(P);
     static thread_local int per_sm_cached = 0, per_sm_dev = -1;
-    if (per_sm_dev != g_props_dev * 8 + NSETS) {
+    if (per_sm_dev != g_props_dev * 4 + NSETS) {
         int n = 0;
         EVOGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem));
         per_sm_cached = n < 1 ? 1 : n;
-        per_sm_dev = g_props_dev * 8 + NSETS;
+        per_sm_dev = g_props_dev * 4 + NSETS;
     }
-    long long grid = (((long long)P + (32 / LPT) - 1) / (32 / LPT) + warps - 1) / warps;
+    long long grid = ((long long)P + warps - 1) / warps;
     const long long cap = (long long)g_sm_count * per_sm_cached;       // one resident wave, grid-stride (as lower_kernel)
     if (grid > cap) grid = cap;
     kern<<<(unsigned)grid, warps * 32, smem, st>>>(a);
     count_launch();
     return check_launch("lower_fast_kernel");
-}
-
-static int launch_lower_fast_any(const Workspace &w, unsigned P, unsigned L, unsigned V, unsigned O, const float *value,
-                                 const int16_t *type, const int16_t *size, int depth, int deep_from, cudaStream_t st) {
-    if (g_lower_lpt == 32)
-        return L <= 32 ? launch_lower_fast<1, 32>(w, P, L, V, O, value, type, size, depth, deep_from, st)
-                       : launch_lower_fast<2, 32>(w, P, L, V, O, value, type, size, depth, deep_from, st);
-    return L <= 32 ? launch_lower_fast<2, 16>(w, P, L, V, O, value, type, size, depth, deep_from, st)
-                   : launch_lower_fast<4, 16>(w, P, L, V, O, value, type, size, depth, deep_from, st);
 }
 
 // split: single-output programs for the K = 16 replay kernel (LOAD + acc-form for operators on leaves)
@@ -174,7 +162,8 @@ static int launch_lower(const Workspace &w, unsigned P, unsigned L, unsigned V, 
     if constexpr (!MULTI) {
         if (split) return launch_lower_t<false, true>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
         if (g_lower_fast && len_stride > 1 && L <= 64)
-            return launch_lower_fast_any(w, P, L, V, O, value, type, size, depth, deep_from, st);
+            return L <= 32 ? launch_lower_fast<1>(w, P, L, V, O, value, type, size, depth, deep_from, st)
+                           : launch_lower_fast<2>(w, P, L, V, O, value, type, size, depth, deep_from, st);
     }
     return launch_lower_t<MULTI, false>(w, P, L, V, O, value, type, size, len_stride, depth, deep_from, st);
 }
@@ -308,7 +297,8 @@ extern "C" int evogp_debug_lower(unsigned popSize, unsigned gpLen, unsigned varL
     EVOGP_CUDA(cudaMemsetAsync(w.prog, 0, prog_bytes(popSize, gpLen), st));
     if (outLen > 1) rc = launch_lower_t<true, false>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, depth, kNoDeepSlots, st);
     else if (use_fast && gpLen <= 64)
-        rc = launch_lower_fast_any(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, depth, df, st);
+        rc = gpLen <= 32 ? launch_lower_fast<1>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, depth, df, st)
+                         : launch_lower_fast<2>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, depth, df, st);
     else rc = launch_lower_t<false, false>(w, popSize, gpLen, varLen, outLen, value, type, subtree_size, (int)gpLen, depth, df, st);
     if (rc) return rc;
     EVOGP_CUDA(cudaMemcpyAsync(programs, w.prog, prog_bytes(popSize, gpLen), cudaMemcpyDeviceToDevice, st));

@@ -20,13 +20,11 @@ namespace evogp {
 
 constexpr int kLowerFallback = -2;
 
-// inclusive prefix sum within groups of W consecutive lanes (sl = lane % W)
-template <int W>
-__device__ __forceinline__ uint32_t group_incl_scan(uint32_t x, int sl) {
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
 #pragma unroll
-    for (int o = 1; o < W; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o, W);
-        if (sl >= o) x += y;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
     }
     return x;
 }
@@ -37,9 +35,9 @@ __device__ __noinline__ float fold_rare(unsigned arity, unsigned fid, float x, f
     return arity == 1u ? fold_unary(unary_slot(fid), x) : fold_binary(binary_slot(fid), x, y);
 }
 
-// per-tree scratch: 4 arrays of NSETS * LPT + 1 words (LPT lanes per tree, each owning NSETS nodes)
-template <int NSETS, int LPT>
-__host__ __device__ constexpr size_t lower_fast_scratch_bytes() { return (size_t)4 * (NSETS * LPT + 1) * 4; }
+// per-warp scratch: 4 arrays of NSETS * 32 + 1 words
+template <int NSETS>
+__host__ __device__ constexpr size_t lower_fast_scratch_bytes() { return (size_t)4 * (NSETS * 32 + 1) * 4; }
 
 // Selector tables of the branch-free emitter, indexed by  idx = f0 << 3 | f1 << 2 | k0 << 1 | k1  (child 0 / child 1 is a
 // function / a constant leaf).  Binary nodes:
@@ -55,18 +53,13 @@ constexpr uint32_t kBinCSel = 0u | (2u << 2) | (1u << 4) | (2u << 6) | (0u << 8)
 static_assert(FM_VV == 8 && FM_VK == 9 && FM_KV == 10 && FM_AK == 5 && FM_AV == 4 && FM_VA == 6 && FM_KA == 7 && FM_SA == 11 &&
               FM_AS == 12 && FM_UA == 1 && FM_UV == 2 && FM_UK == 3, "emitter tables follow program.cuh's form numbers");
 
-// LPT lanes per tree (32: one tree per warp; 16: two trees per warp, each half-warp with its own pointers and scratch),
-// each lane owning nodes sl, sl + LPT, ... (NSETS of them).  Returns, per tree, the operand-stack height the program
-// needs (>= 0), -1 for a program that was replaced by C_NAN, or kLowerFallback when the row is outside the fast class
-// (whatever was written is to be overwritten by the generic pass).
-template <int NSETS, int LPT>
-__device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val, const int16_t *typ, const int16_t *size,
+// Returns the operand-stack height the program needs (>= 0), -1 for a program that was replaced by C_NAN, or
+// kLowerFallback when the row is outside the fast class (nothing was written).
+template <int NSETS>
+__device__ __forceinline__ int lower_fast_tree(const int lane, const float *val, const int16_t *typ, const int16_t *size,
                                                const int L, const int Lp, const int V, const int depth_budget,
                                                const int deep_from, const bool fold, uint2 *out, uint32_t *sm_) {
-    static_assert(LPT == 32 || LPT == 16, "one or two trees per warp");
-    constexpr int CAP = NSETS * LPT + 1;
-    const int lane = lane_ & (LPT - 1);                        // lane within the tree's group
-    const uint32_t gmask = LPT == 32 ? 0xffffffffu : (0xFFFFu << (lane_ & 16));
+    constexpr int CAP = NSETS * 32 + 1;
     constexpr uint32_t POISON = 0x4000u;   // size of a slot beyond the row: any father reaching it fails its size check
     // volatile: other lanes write these words between this lane's accesses (a restrict-qualified or plain pointer lets
     // the compiler reuse a child's type word it loaded before the folding pass rewrote it)
@@ -76,23 +69,18 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
     uint32_t t[NSETS], s[NSETS], v[NSETS];
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
-        const int i = lane + LPT * k;
+        const int i = lane + 32 * k;
         const bool in = i < L;
         t[k] = in ? (uint32_t)(uint16_t)__ldg(typ + i) : 0u;
         s[k] = in ? (uint32_t)(uint16_t)__ldg(size + i) : 0u;
         v[k] = in ? __float_as_uint(__ldg(val + i)) : 0u;
     }
-    int len = (int)__shfl_sync(0xffffffffu, s[0], 0, LPT);
-    const bool bad_len = len < 1 || len > L;
-    if (LPT == 32 && bad_len) return kLowerFallback;
-    if (bad_len) len = 0;                                      // the other tree of the warp goes on: this one is inert
-    // warp-uniform: node sets beyond the longer tree of the warp are skipped
-    int nk = (len + LPT - 1) / LPT;
-    if (LPT == 16) nk = max(nk, __shfl_xor_sync(0xffffffffu, nk, 16));
-    nk = max(nk, 1);
+    const int len = (int)__shfl_sync(0xffffffffu, s[0], 0);
+    if (len < 1 || len > L) return kLowerFallback;
+    const int nk = (NSETS > 1 && len > 32) ? NSETS : 1;       // warp-uniform: short trees skip the second node set
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
-        const int i = lane + LPT * k;
+        const int i = lane + 32 * k;
         const bool valid = i < len;
         if (!valid) { t[k] = 0u; s[k] = 1u; v[k] = 0u; }      // a lone leaf as far as this lane's own checks go
         TS[i] = valid ? (t[k] | (s[k] << 16)) : (POISON << 16);
@@ -110,7 +98,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
     for (int k = 0; k < NSETS; ++k) {
         ar[k] = 0u; w0[k] = 0u; w1[k] = 0u; c1s[k] = 0u;
         if (k < nk) {
-            const int i = lane + LPT * k;
+            const int i = lane + 32 * k;
             const uint32_t a = t[k] > 1u ? t[k] - 1u : 0u;      // arity_of(t, false): the type is NOT masked in single-output mode
             const uint32_t x0 = TS[i + 1];
             const uint32_t c1 = min((uint32_t)(i + 1) + (x0 >> 16), (uint32_t)(CAP - 1));
@@ -120,12 +108,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
             ar[k] = a; w0[k] = x0; w1[k] = x1; c1s[k] = c1;
         }
     }
-    const bool bad_tree = bad_len || (__ballot_sync(0xffffffffu, bad) & gmask) != 0u;
-    if (LPT == 32 && bad_tree) return kLowerFallback;
-    if (bad_tree) {          // two trees per warp: this one waits for the generic pass as a row of inert leaves
-#pragma unroll
-        for (int k = 0; k < NSETS; ++k) { ar[k] = 0u; s[k] = 1u; t[k] = 0u; }
-    }
+    if (__any_sync(0xffffffffu, bad)) return kLowerFallback;
     // ---- constant folding, one level (lower.cuh): a function of constant leaves becomes a constant leaf that keeps its
     //      size; decisions come from the children gathered above, i.e. from the untouched row ----
     unsigned fid[NSETS];
@@ -139,7 +122,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
                 const bool k0 = (w0[k] & 0xFFFFu) == 1u, k1 = (w1[k] & 0xFFFFu) == 1u;
                 const bool can = (ar[k] == 2u && k0 && k1) || (ar[k] == 1u && k0);
                 if (can) {
-                    const float x = __uint_as_float(VB[lane + LPT * k + 1]), y = __uint_as_float(VB[c1s[k]]);
+                    const float x = __uint_as_float(VB[lane + 32 * k + 1]), y = __uint_as_float(VB[c1s[k]]);
                     const unsigned b = fid[k] - (unsigned)F_ADD;
                     float r;
                     if (ar[k] == 2u && b < 4u) {   // + - * / without a branch: the interpreter's own operator bodies, selected
@@ -149,8 +132,8 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
                         r = fold_rare(ar[k], fid[k], x, y);
                     }
                     t[k] = NT_CONST; v[k] = __float_as_uint(r); ar[k] = 0u;
-                    TS[lane + LPT * k] = (uint32_t)NT_CONST | (s[k] << 16);
-                    VB[lane + LPT * k] = v[k];
+                    TS[lane + 32 * k] = (uint32_t)NT_CONST | (s[k] << 16);
+                    VB[lane + 32 * k] = v[k];
                 }
                 any |= can;
             }
@@ -160,19 +143,19 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
 #pragma unroll
             for (int k = 0; k < NSETS; ++k) {
                 if (k < nk) {
-                    w0[k] = TS[lane + LPT * k + 1];
+                    w0[k] = TS[lane + 32 * k + 1];
                     w1[k] = TS[c1s[k]];
                 }
             }
         }
     }
-    const bool leaf_tree = __shfl_sync(0xffffffffu, ar[0], 0, LPT) == 0u;
-    if (leaf_tree) {   // the tree is a single leaf (with two trees per warp its lanes stay along, inert: no node is a function)
+    const uint32_t ar_root = __shfl_sync(0xffffffffu, ar[0], 0);
+    if (ar_root == 0u) {   // the tree is a single leaf
         if (lane == 0) {
             out[0] = leaf_instr(C_LOAD_V, C_LOAD_K, leaf_of((int)t[0], __uint_as_float(v[0]), V), 0);
             if (Lp > 1) out[1] = mk2(C_END, 0);
         }
-        if (LPT == 32) return 0;
+        return 0;
     }
     // ---- instruction slots each node contributes itself (two for `const op const`), exclusive prefix sum ----
     uint32_t idx[NSETS], m[NSETS], mx[NSETS];
@@ -185,11 +168,11 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
             idx[k] = (t0 > 1u ? 8u : 0u) | (t1 > 1u ? 4u : 0u) | (t0 == 1u ? 2u : 0u) | (t1 == 1u ? 1u : 0u);
             if (ar[k] == 1u) idx[k] &= 10u;                      // a unary node has no second child (w1 is whatever follows its subtree)
             m[k] = (ar[k] != 0u ? 1u : 0u) + ((ar[k] == 2u && idx[k] == 3u) ? 1u : 0u);
-            const uint32_t incl = group_incl_scan<LPT>(m[k], lane);
+            const uint32_t incl = warp_incl_scan(m[k], lane);
             mx[k] = carry + incl - m[k];
-            carry += __shfl_sync(0xffffffffu, incl, LPT - 1, LPT);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        M[lane + LPT * k] = mx[k];
+        M[lane + 32 * k] = mx[k];
     }
     const uint32_t total = carry;
     if (lane == 0) M[CAP - 1] = total;
@@ -202,7 +185,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
     for (int k = 0; k < NSETS; ++k) {
         mend[k] = 0u;
         if (k < nk) {
-            const int i = lane + LPT * k;
+            const int i = lane + 32 * k;
             const uint32_t e = (uint32_t)i + s[k];                 // one past this subtree
             mend[k] = M[e];
             if (ar[k] == 2u && idx[k] >= 12u) {
@@ -221,9 +204,9 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
     for (int k = 0; k < NSETS; ++k) {
         d[k] = 0u;
         if (k < nk) {
-            const uint32_t incl = group_incl_scan<LPT>(D[lane + LPT * k], lane);
+            const uint32_t incl = warp_incl_scan(D[lane + 32 * k], lane);
             d[k] = carry + incl;
-            carry += __shfl_sync(0xffffffffu, incl, LPT - 1, LPT);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     // ---- emit: one instruction per function node (two for `const op const`); form and operand placement come from
@@ -232,7 +215,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) {
         if (k < nk && ar[k] != 0u) {
-            const int i = lane + LPT * k;
+            const int i = lane + 32 * k;
             const uint32_t pending = d[k] >> 16, st = d[k] & 0xFFFFu;       // values alive when this subtree begins; its first slot
             const uint32_t live_push = pending << I_PUSH_SHIFT;             // a fresh value saves acc into slot pending - 1 (field = slot + 1)
             const uint32_t own = st + (mend[k] - mx[k]) - 1u;
@@ -274,11 +257,10 @@ __device__ __forceinline__ int lower_fast_tree(const int lane_, const float *val
             out[own] = mk2(w, c);
         }
     }
-    if (lane == 0 && !leaf_tree && (int)total < Lp) out[total] = mk2(C_END, 0);
-    const int need = (int)__reduce_max_sync(gmask, my_max);
-    __syncwarp();
-    if (bad_tree) return kLowerFallback;
+    if (lane == 0 && (int)total < Lp) out[total] = mk2(C_END, 0);
+    const int need = (int)__reduce_max_sync(0xffffffffu, my_max);
     if (need > depth_budget) {   // cannot happen for well-formed rows (stack_depth_bound); fail safe
+        __syncwarp();
         if (lane == 0) {
             out[0] = mk2(C_NAN, 0);
             if (Lp > 1) out[1] = mk2(C_END, 0);
@@ -297,42 +279,30 @@ __device__ __noinline__ void lower_generic_row(int lane, const float *val, const
     lower_tree<false, false>(Lanes{lane, 32}, val, typ, srow, len, L, Lp, V, O, depth_budget, out, k, true, deep_from, fold);
 }
 
-template <int NSETS, int LPT>
+template <int NSETS>
 __host__ __device__ inline size_t lower_fast_per_warp(int L) {
-    const size_t a = (32 / LPT) * lower_fast_scratch_bytes<NSETS, LPT>(), b = lower_scratch_bytes(L);
+    const size_t a = lower_fast_scratch_bytes<NSETS>(), b = lower_scratch_bytes(L);
     return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
-// LPT = 32: one warp per tree; LPT = 16: two trees per warp (most trees are shorter than 32 nodes, and a warp
-// instruction costs the same whether 26 or 32 lanes have a node).  Grid-stride over the population.  Requires packed
-// subtree_size rows (rows_have_sizes).
-template <int NSETS, int LPT>
+// one warp per tree, grid-stride over the population.  Requires packed subtree_size rows (rows_have_sizes).
+template <int NSETS>
 __global__ void __launch_bounds__(256) lower_fast_kernel(LowerArgs g) {
     extern __shared__ __align__(16) unsigned char lower_smem[];
-    constexpr int TPW = 32 / LPT;                                          // trees per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    unsigned char *scratch = lower_smem + warp * lower_fast_per_warp<NSETS, LPT>(g.L);
-    uint32_t *mine = reinterpret_cast<uint32_t *>(scratch + (lane / LPT) * lower_fast_scratch_bytes<NSETS, LPT>());
+    unsigned char *scratch = lower_smem + warp * lower_fast_per_warp<NSETS>(g.L);
     lower_zero_scheduler_words(g);
-    const int ngroups = (g.P + TPW - 1) / TPW;
-    for (int grp = blockIdx.x * nwarp + warp; grp < ngroups; grp += gridDim.x * nwarp) {
-        // the last group of an odd population lowers its last tree twice (identical stores)
-        const int n = min(grp * TPW + lane / LPT, g.P - 1);
+    for (int n = blockIdx.x * nwarp + warp; n < g.P; n += gridDim.x * nwarp) {
         const float *val = g.value + (size_t)n * g.L;
         const int16_t *typ = g.type + (size_t)n * g.L, *srow = g.size + (size_t)n * g.L;
         uint2 *out = g.prog + (size_t)n * g.Lp;
-        const int rc = lower_fast_tree<NSETS, LPT>(lane, val, typ, srow, g.L, g.Lp, g.V, g.depth_budget, g.deep_from, g.fold != 0, out, mine);
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < TPW; ++h) {     // rows outside the fast class: the generic pass, the whole warp on one row
-            if (__shfl_sync(0xffffffffu, rc, h * LPT) == kLowerFallback) {
-                const int m = min(grp * TPW + h, g.P - 1);
-                const int16_t *sr = g.size + (size_t)m * g.L;
-                lower_generic_row(lane, g.value + (size_t)m * g.L, g.type + (size_t)m * g.L, sr, (int)__ldg(sr), g.L, g.Lp, g.V, g.O,
-                                  g.depth_budget, g.prog + (size_t)m * g.Lp, scratch, g.deep_from, g.fold != 0);
-                __syncwarp();
-            }
+        const int rc = lower_fast_tree<NSETS>(lane, val, typ, srow, g.L, g.Lp, g.V, g.depth_budget, g.deep_from, g.fold != 0, out,
+                                              reinterpret_cast<uint32_t *>(scratch));
+        if (rc == kLowerFallback) {
+            __syncwarp();
+            lower_generic_row(lane, val, typ, srow, (int)__ldg(srow), g.L, g.Lp, g.V, g.O, g.depth_budget, out, scratch, g.deep_from, g.fold != 0);
         }
+        __syncwarp();
     }
 }
 
