@@ -24,8 +24,8 @@ def depth_schedule(max_tree_len, using_funcs, max_layer_cnt, layer_leaf_prob, de
     arity = max((func_arity(FUNCS_NAMES.index(f)) for f in using_funcs), default=0)
     need = full_tree_len(arity, max_layer_cnt)
     assert max_tree_len >= need, (
-        f"max_tree_len={max_tree_len} is too small\nmax_tree_len should >={need}\n"
-        f"as the max arity of funcs is {arity} and the max layer is {max_layer_cnt}."
+        f"a full tree of {max_layer_cnt} layers over functions of arity up to {arity} has {need} nodes; "
+        f"max_tree_len {max_tree_len} cannot hold it"
     )
     inner = max_layer_cnt - 1
     return torch.tensor([layer_leaf_prob] * inner + [1.0] * (MAX_FULL_DEPTH - inner), dtype=torch.float32, device=device)
@@ -51,24 +51,24 @@ class GenerateDescriptor:
         self._ctor_kwargs = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
         dev = _native.device()
 
-        assert max_tree_len <= MAX_STACK, f"max_tree_len={max_tree_len} is too large, MAX_STACK={MAX_STACK}"
-        assert isinstance(input_len, int) and input_len > 0, "input_len should be a positive integer"
-        assert isinstance(output_len, int) and output_len > 0, "output_len should be a positive integer"
-        assert 0.0 <= const_prob <= 1.0, "const_prob should be in [0.0, 1.0]"
-        assert 0.0 <= out_prob <= 1.0, "out_prob should be in [0.0, 1.0]"
+        assert max_tree_len <= MAX_STACK, f"max_tree_len {max_tree_len} exceeds the kernels' row limit ({MAX_STACK})"
+        assert isinstance(input_len, int) and input_len > 0, "input_len: expected a positive int"
+        assert isinstance(output_len, int) and output_len > 0, "output_len: expected a positive int"
+        assert 0.0 <= const_prob <= 1.0, "const_prob is a probability: 0 <= const_prob <= 1"
+        assert 0.0 <= out_prob <= 1.0, "out_prob is a probability: 0 <= out_prob <= 1"
         if output_len > 1 and out_prob == 0.0:
             warnings.warn(f"output_len={output_len} > 1, but out_prob={out_prob} is 0.0.")
 
         if depth2leaf_probs is None:
-            assert max_layer_cnt is not None, "max_layer_cnt should not be None when depth2leaf_probs is None"
-            assert layer_leaf_prob is not None, "layer_leaf_prob should not be None when depth2leaf_probs is None"
+            assert max_layer_cnt is not None, "give either depth2leaf_probs or max_layer_cnt (+ layer_leaf_prob)"
+            assert layer_leaf_prob is not None, "layer_leaf_prob is needed to build depth2leaf_probs from max_layer_cnt"
             funcs = list(using_funcs) if using_funcs is not None else []
             depth2leaf_probs = depth_schedule(max_tree_len, funcs, max_layer_cnt, layer_leaf_prob, dev)
 
         self.roulette_ufuncs = self.roulette_bfuncs = self.roulette_tfuncs = None
         if roulette_funcs is None:
-            assert using_funcs is not None, "func_prob should not be None when roulette_funcs is None"
-            assert isinstance(using_funcs, (dict, list)), "func_prob should be a dictionary or a list"
+            assert using_funcs is not None, "give either roulette_funcs or using_funcs"
+            assert isinstance(using_funcs, (dict, list)), "using_funcs: a list of function names, or a dict name -> weight"
             weights = using_funcs if isinstance(using_funcs, dict) else {f: 1.0 for f in using_funcs}
             prob = dict2prob(weights)
             roulette_funcs = torch.cumsum(prob, dim=0, dtype=torch.float32).to(dev)
@@ -83,8 +83,8 @@ class GenerateDescriptor:
             self.roulette_ufuncs = class_roulette(Func.UF_START, Func.END)
 
         if const_samples is None:
-            assert const_range is not None, "const_range should not be None when const_samples is None"
-            assert sample_cnt is not None, "sample_cnt should not be None when const_samples is None"
+            assert const_range is not None, "give either const_samples or const_range (+ sample_cnt)"
+            assert sample_cnt is not None, "sample_cnt is needed to draw constants from const_range"
             lo, hi = const_range
             const_samples = torch.rand(sample_cnt, device=dev) * (hi - lo) + lo
         if isinstance(const_samples, list):
@@ -94,9 +94,9 @@ class GenerateDescriptor:
         roulette_funcs = to_cuda_f32(roulette_funcs, dev).to(torch.float32).contiguous()
         const_samples = to_cuda_f32(const_samples, dev).to(torch.float32).contiguous()
         assert depth2leaf_probs.shape == (MAX_FULL_DEPTH,), \
-            f"depth2leaf_probs shape should be ({MAX_FULL_DEPTH}), but got {depth2leaf_probs.shape}"
-        assert roulette_funcs.shape == (Func.END,), f"roulette_funcs shape should be ({Func.END}), but got {roulette_funcs.shape}"
-        assert const_samples.dim() == 1, f"const_samples dim should be 1, but got {const_samples.dim()}"
+            f"depth2leaf_probs must hold {MAX_FULL_DEPTH} probabilities, got shape {tuple(depth2leaf_probs.shape)}"
+        assert roulette_funcs.shape == (Func.END,), f"roulette_funcs must hold {Func.END} cumulative probabilities, got shape {tuple(roulette_funcs.shape)}"
+        assert const_samples.dim() == 1, f"const_samples must be one-dimensional, got {const_samples.dim()} dimensions"
 
         self.max_tree_len = max_tree_len
         self.input_len = input_len
