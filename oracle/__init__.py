@@ -11,6 +11,7 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 from .oracle import (  # noqa: F401
     build,
     build_ref,
+    build_reference_package,
     lib,
     ref_gpu,
     ref_gpu_available,

@@ -44,6 +44,30 @@ def build_ref(force=False):
     return _REF_SO
 
 
+def build_reference_package(force=False):
+    """Installs the reference's own package, unmodified, into the git-ignored baseline/_ref (what `bench.py --impl
+    reference` and tests/test_dropin.py run): pip install from a copy of /root/reference (the tree is read-only and the
+    build writes into it), offline, no dependency resolution.  ~4 minutes (its CUDA extension); skipped when already
+    there or where /root/reference does not exist (the GPU box uses the prebuilt files)."""
+    import shutil
+    import sys
+    import tempfile
+
+    target = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+    if os.path.isdir(os.path.join(target, "evogp")) and not force:
+        return target
+    if not os.path.isdir(_REFERENCE_ROOT):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "refsrc")
+        shutil.copytree(_REFERENCE_ROOT, src)
+        env = dict(os.environ, TORCH_CUDA_ARCH_LIST="10.0a")
+        subprocess.check_call([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps",
+                               "--find-links", "/opt/wheelhouse", "--target", target, src], env=env,
+                              stdout=subprocess.DEVNULL)
+    return target
+
+
 def lib():
     global _lib
     if _lib is None:
