@@ -6,6 +6,7 @@
 #include "fastpath_k8.inc"
 #include "fastpath_k8_tmem.inc"
 #include "fastpath_k16_tmem.inc"
+#include "fastpath_k8_multi.inc"
 
 namespace evogp {
 
@@ -430,6 +431,23 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
                                      : "r"(xl_addr), "r"(npb), "r"(stack_base)
                                      : "memory");
                     }
+                    if (status == 0) break;
+                    pc = (int)((pc_addr - prog_base) >> 3);
+                    if (step()) break;
+                    pc_addr = prog_base + ((uint32_t)pc << 3);
+                }
+            } else if constexpr (K == 8 && MULTI && !ROWWISE) {
+                // PTX loop for multi-output programs (fastpath_k8_multi.inc): leaf-operand forms, outs[] += in shared memory;
+                // C_IF3 and the rare operators come back here one instruction at a time
+                const uint32_t prog_base = smem_u32(prog), outs_base = smem_u32(outs + lane_off);
+                uint32_t pc_addr = prog_base, status;
+                const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
+                for (;;) {
+                    asm volatile(EVOGP_FASTPATH_K8_MULTI_ASM
+                                 : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                   "+f"(acc[6]), "+f"(acc[7]), "+r"(pc_addr), "=r"(status)
+                                 : "r"(xl_addr), "r"(npb), "r"(outs_base)
+                                 : "memory");
                     if (status == 0) break;
                     pc = (int)((pc_addr - prog_base) >> 3);
                     if (step()) break;
