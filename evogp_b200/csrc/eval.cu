@@ -8,8 +8,10 @@
 // Two kernels (a single fused kernel — each warp lowering its own tree into shared memory before replaying
 // it — was built and measured: same total time at best, because lowering + replay code together overflow the
 // SM instruction cache: sm__icc_request_hit_rate 97 % -> 70 %, profiles/r1_fused_kernel_icache.txt):
-//   lower_kernel  (lower.cuh)  packed rows -> accumulator-machine programs, 8 B/slot; one warp per tree
-//   replay_kernel (here)       persistent CTAs; each WARP owns one tree at a time,
+//   lower_kernel / lower_fast_kernel (lower.cuh, lower_fast.cuh)  packed rows -> accumulator-machine programs, 8 B/slot;
+//        one warp per tree; the register-resident fast pass serves single-output rows of max_tree_len <= 64
+//   replay_kernel (replay.cuh; this file instantiates the plain flavour, eval_exchange.cu / eval_acc.cu the others)
+//        persistent CTAs; each WARP owns one tree at a time,
 //        lanes own datapoints (K per lane, float4-vectorised), so the opcode
 //        dispatch is warp-uniform.  The next tree's program row is pulled into
 //        shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) while the
@@ -21,8 +23,8 @@
 //        Single-output programs keep their operand stack in TENSOR MEMORY (TSTK):
 //        tcgen05.st / tcgen05.ld of one K-column slot per save / restore, no MMA
 //        involved; K = 16 datapoints per lane in one 32-warp CTA per SM, K = 8 in
-//        four 8-warp CTAs.  Multi-GPU: the fitness all-gather is
-//        fused into the final store (Scatter: peer-mapped buffers over NVLink).
+//        four 8-warp CTAs.  Multi-output programs: their own PTX loop (K = 8), outs[] in shared
+//        memory.  Multi-GPU: evogp_push_fitness after this kernel, or the exchange flavour of it.
 #include "replay.cuh"
 #include "lower_fast.cuh"
 
