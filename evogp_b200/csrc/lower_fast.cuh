@@ -115,6 +115,7 @@ __device__ __forceinline__ int lower_fast_tree(const int lane, const float *val,
 #pragma unroll
     for (int k = 0; k < NSETS; ++k) fid[k] = __float2uint_rz(__uint_as_float(v[k]));   // forward.cu:108 `(unsigned int)node_value`
     if (fold) {
+        __syncwarp();          // every lane has read its children's words: the folding stores below may overwrite them
         bool any = false;
 #pragma unroll
         for (int k = 0; k < NSETS; ++k) {
