@@ -123,7 +123,8 @@ __device__ __forceinline__ int lower_fast_tree(const int lane, const float *val,
                 const bool k0 = (w0[k] & 0xFFFFu) == 1u, k1 = (w1[k] & 0xFFFFu) == 1u;
                 const bool can = (ar[k] == 2u && k0 && k1) || (ar[k] == 1u && k0);
                 if (can) {
-                    const float x = __uint_as_float(VB[lane + 32 * k + 1]), y = __uint_as_float(VB[c1s[k]]);
+                    const float x = __uint_as_float(VB[lane + 32 * k + 1]);
+                    const float y = ar[k] == 2u ? __uint_as_float(VB[c1s[k]]) : 0.0f;   // a unary node has no second child to read
                     const unsigned b = fid[k] - (unsigned)F_ADD;
                     float r;
                     if (ar[k] == 2u && b < 4u) {   // + - * / without a branch: the interpreter's own operator bodies, selected
