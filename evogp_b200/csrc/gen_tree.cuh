@@ -6,18 +6,20 @@
 
 namespace evogp {
 
-// kernel.h:160-172: low 32 bits of 64-bit FNV-1a over the bytes of {n, k1, k2}
+// kernel.h:160-172: low 32 bits of 64-bit FNV-1a over the bytes of {n, k1, k2}.  Only the low word is used, and the low word
+// of (h ^ byte) * prime depends on the low words alone: the hash runs in 32-bit arithmetic (offset basis
+// 0xCBF29CE484222325, prime 0x100000001B3 -> their low halves).
 __device__ __forceinline__ uint32_t tree_seed(uint32_t n, uint32_t k1, uint32_t k2) {
-    uint64_t h = 14695981039346656037ULL;
+    uint32_t h = 0x84222325u;
     const uint32_t a[3] = {n, k1, k2};
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            h ^= (uint64_t)((a[i] >> (8 * b)) & 0xFFu);
-            h *= 1099511628211ULL;
+            h ^= (a[i] >> (8 * b)) & 0xFFu;
+            h *= 0x000001B3u;
         }
-    return (uint32_t)h;
+    return h;
 }
 
 // thrust::random::taus88 (kernel.h:20): three LFSRs, all seeded with the same word
@@ -171,15 +173,21 @@ __device__ __forceinline__ uint32_t fastmod_u32(uint32_t x, uint64_t M, uint32_t
 // id in [20:16] and, while their frame is open, the index of the enclosing function node in [31:21].
 // s_leaf: 16 floats (depth -> leaf probability, 2.0 beyond MAX_FULL_DEPTH); s_roul: 32 floats (cumulative roulette padded
 // with +inf); mono: the roulette is non-decreasing (binary search allowed).  Returns the tree length (0 when !active).
-__device__ __forceinline__ int grow_tree_packed(uint32_t seed, bool active, const float *s_leaf, const float *s_roul, bool mono,
-                                                uint32_t V, uint32_t S, uint64_t MV, uint64_t MS, float constProb, int L,
-                                                uint32_t *row) {
-    int cnt = 0, d = active ? 0 : -1;
-    uint32_t owed = 1;                 // children still owed per depth, 2 bits each (arity <= 3); root frame {1, 0}
-    uint32_t cur = 0;                  // the function node whose children are being generated (depth >= 1)
+// One tree being grown: the registers of the loop below (generate_fast_kernel and nextgen grow a tree to the end with
+// grow_tree_packed; generate_balanced_kernel steps 32 of them side by side and re-arms a lane when its tree is done).
+struct PackedGrowth {
+    int cnt, d;
+    uint32_t owed;                     // children still owed per depth, 2 bits each (arity <= 3); root frame {1, 0}
+    uint32_t cur;                      // the function node whose children are being generated (depth >= 1)
     Taus88State st;
-    st.z1 = st.z2 = st.z3 = seed;
-    while (d >= 0 && cnt < L) {
+    __device__ __forceinline__ void start(uint32_t seed, bool active) {
+        cnt = 0; d = active ? 0 : -1; owed = 1; cur = 0;
+        st.z1 = st.z2 = st.z3 = seed;
+    }
+    __device__ __forceinline__ bool growing(int L) const { return d >= 0 && cnt < L; }
+    // one node (generate.cu:58-128 of the reference, one iteration of its loop)
+    __device__ __forceinline__ void step(const float *s_leaf, const float *s_roul, bool mono, uint32_t V, uint32_t S, uint64_t MV,
+                                         uint64_t MS, float constProb, uint32_t *row) {
         owed -= 1u << (2 * d);                                     // cd.childs-- (generate.cu:61)
         const float leafp = s_leaf[d];
         // draws: u (leaf test); then r (roulette) or u (constant test) - the same word; then, for a leaf only, a raw word.
@@ -226,20 +234,60 @@ __device__ __forceinline__ int grow_tree_packed(uint32_t seed, bool active, cons
             }
         }
     }
-    for (; d > 0; --d) {   // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open
-        const uint32_t w = row[cur];
-        row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
-        cur = w >> 21;
+    // row full before the tree closed (a descriptor check_tree_length would have refused): close what is open.
+    // Returns the tree length (0 for a lane that never had a tree).
+    __device__ __forceinline__ int finish(uint32_t *row) {
+        for (; d > 0; --d) {
+            const uint32_t w = row[cur];
+            row[cur] = (w & 0x001FFFFFu) | ((uint32_t)(cnt - (int)cur) << 4);
+            cur = w >> 21;
+        }
+        return cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
     }
-    return cnt > 0 ? (int)((row[0] >> 4) & 0xFFF) : 0;
+};
+
+__device__ __forceinline__ int grow_tree_packed(uint32_t seed, bool active, const float *s_leaf, const float *s_roul, bool mono,
+                                                uint32_t V, uint32_t S, uint64_t MV, uint64_t MS, float constProb, int L,
+                                                uint32_t *row) {
+    PackedGrowth t;
+    t.start(seed, active);
+    while (t.growing(L)) t.step(s_leaf, s_roul, mono, V, S, MV, MS, constProb, row);
+    return t.finish(row);
 }
 
-// packed node word -> value bits, node type, subtree size
+// packed node word -> value bits, node type, subtree size.  Branch-free (the constant table is read at index 0 for the
+// other node types); a zero word - the padding behind a tree - decodes to three zeros.
 __device__ __forceinline__ void decode_packed_node(uint32_t w, const float *consts, uint32_t &v, uint32_t &t, uint32_t &sz) {
     t = w & 7u;
     sz = (w >> 4) & 0xFFFu;
     const uint32_t code = w >> 16;
-    v = t == NT_CONST ? __float_as_uint(__ldg(consts + code)) : __float_as_uint((float)(t == NT_VAR ? code : (code & 31u)));
+    const float cv = __ldg(consts + (t == NT_CONST ? code : 0u));
+    const float fv = (float)(t == NT_VAR ? code : (code & 31u));
+    v = __float_as_uint(t == NT_CONST ? cv : fv);
+}
+
+// One packed row (len valid words at src, in shared memory) -> one zero-filled row of the three output arrays, by a warp.
+__device__ __forceinline__ void write_packed_row(const uint32_t *src, int len, int lane, int L, const float *consts, float *ov,
+                                                 int16_t *ot, int16_t *os) {
+    if ((L & 1) == 0) {
+        for (int j = lane * 2; j < L; j += 64) {
+            const uint32_t w0 = j < len ? src[j] : 0u, w1 = j + 1 < len ? src[j + 1] : 0u;
+            uint32_t v0, t0, z0, v1, t1, z1;
+            decode_packed_node(w0, consts, v0, t0, z0);
+            decode_packed_node(w1, consts, v1, t1, z1);
+            *reinterpret_cast<uint2 *>(ov + j) = make_uint2(v0, v1);
+            *reinterpret_cast<uint32_t *>(ot + j) = t0 | (t1 << 16);
+            *reinterpret_cast<uint32_t *>(os + j) = z0 | (z1 << 16);
+        }
+    } else {
+        for (int j = lane; j < L; j += 32) {
+            uint32_t v, t, z;
+            decode_packed_node(j < len ? src[j] : 0u, consts, v, t, z);
+            ov[j] = __uint_as_float(v);
+            ot[j] = (int16_t)t;
+            os[j] = (int16_t)z;
+        }
+    }
 }
 
 }  // namespace evogp

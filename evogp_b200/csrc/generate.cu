@@ -153,37 +153,99 @@ __global__ void __launch_bounds__(256, 3) generate_fast_kernel(GenArgs g) {
     // ---- this warp's 32 rows leave through coalesced, zero-filled stores ----
     const unsigned first = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
     const uint32_t *rows = gsm + (size_t)(threadIdx.x & ~31) * pitch;
-    auto decode = [&](uint32_t w, uint32_t &v, uint32_t &t, uint32_t &sz) { decode_packed_node(w, g.consts, v, t, sz); };
     for (int r = 0; r < 32; ++r) {
         const unsigned tree = first + r;
         if (tree >= g.P) break;
         const int rl = __shfl_sync(0xffffffffu, len, r);
-        const uint32_t *src = rows + (size_t)r * pitch;
-        float *ov = g.ovalue + (size_t)tree * L;
-        int16_t *ot = g.otype + (size_t)tree * L;
-        int16_t *os = g.osize + (size_t)tree * L;
-        if ((L & 1) == 0) {
-            for (int j = lane * 2; j < L; j += 64) {
-                uint32_t v0 = 0, t0 = 0, z0 = 0, v1 = 0, t1 = 0, z1 = 0;
-                if (j < rl) decode(src[j], v0, t0, z0);
-                if (j + 1 < rl) decode(src[j + 1], v1, t1, z1);
-                *reinterpret_cast<uint2 *>(ov + j) = make_uint2(v0, v1);
-                *reinterpret_cast<uint32_t *>(ot + j) = t0 | (t1 << 16);
-                *reinterpret_cast<uint32_t *>(os + j) = z0 | (z1 << 16);
-            }
-        } else {
-            for (int j = lane; j < L; j += 32) {
-                uint32_t v = 0, t = 0, z = 0;
-                if (j < rl) decode(src[j], v, t, z);
-                ov[j] = __uint_as_float(v);
-                ot[j] = (int16_t)t;
-                os[j] = (int16_t)z;
-            }
+        write_packed_row(rows + (size_t)r * pitch, rl, lane, L, g.consts, g.ovalue + (size_t)tree * L, g.otype + (size_t)tree * L,
+                         g.osize + (size_t)tree * L);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// generate_balanced_kernel - the same growth, lanes re-armed.
+//
+// In generate_fast_kernel a warp runs until the longest of its 32 trees is done: tree lengths spread from 1 to
+// max_tree_len, so 14.6 of 32 lanes are active on average (ncu, profiles/r2_genetic_final_ncu.txt) and, at 100000 trees,
+// the whole launch is one wave whose duration is that of its slowest warp.  Here a warp owns a contiguous span of
+// `per_warp` trees (more than 32): the 32 lanes start the first 32; whenever lanes finish (one ballot per node step) the
+// warp writes their rows out - coalesced, one row at a time, as before - and hands them the next trees of the span.  The
+// grid is a multiple of the SM count, so every SM carries the same number of spans.  A tree's nodes depend on its index
+// alone (seed = f(index, keys)): the output is bit-identical to the other kernels'.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) generate_balanced_kernel(GenArgs g) {
+    extern __shared__ uint32_t gsm[];
+    __shared__ float s_leaf[16];
+    __shared__ float s_roul[32];
+    __shared__ int s_mono;
+    const int pitch = g.pitch, L = (int)g.L;
+    if (threadIdx.x < 16) s_leaf[threadIdx.x] = threadIdx.x < kMaxFullDepth ? g.depth2leaf[threadIdx.x] : 2.0f;
+    if (threadIdx.x < 32) s_roul[threadIdx.x] = threadIdx.x < F_END ? g.roulette[threadIdx.x] : __int_as_float(0x7f800000);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mono = 1;
+        for (int i = 1; i < F_END; ++i) mono &= s_roul[i] >= s_roul[i - 1];
+        s_mono = mono;
+    }
+    __syncthreads();
+    const bool mono = s_mono != 0;
+    const int lane = threadIdx.x & 31;
+    uint32_t *row = gsm + (size_t)threadIdx.x * pitch;
+    const uint32_t *rows = gsm + (size_t)(threadIdx.x & ~31) * pitch;
+    const uint32_t V = g.V, S = g.S;
+    const uint64_t MV = g.magicV, MS = g.magicS;
+    const float constProb = g.constProb;
+    const uint32_t k0 = g.keys[0], k1 = g.keys[1];
+
+    const unsigned span = (unsigned)g.trees_per_block;                       // trees per WARP in this kernel
+    const unsigned wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long b0 = (unsigned long long)wid * span;
+    const unsigned t0 = b0 < g.P ? (unsigned)b0 : g.P;
+    const unsigned t1 = g.P - t0 < span ? g.P : t0 + span;
+    unsigned next = t0 + 32 < t1 ? t0 + 32 : t1;                             // first tree of the span not handed out yet
+    unsigned mine = t0 + (unsigned)lane;                                     // the tree this lane is growing
+    bool busy = mine < t1;
+    PackedGrowth t;
+    t.start(tree_seed(mine, k0, k1), busy);
+    while (__any_sync(0xffffffffu, busy)) {
+        if (t.growing(L)) t.step(s_leaf, s_roul, mono, V, S, MV, MS, constProb, row);
+        const bool fin = busy && !t.growing(L);
+        unsigned done = __ballot_sync(0xffffffffu, fin);
+        if (done == 0u) continue;
+        const int len = fin ? t.finish(row) : 0;
+        __syncwarp();
+        const unsigned rank = __popc(done & ((1u << lane) - 1u));
+        const unsigned handed = __popc(done);
+        while (done) {                                                      // rows of the finished lanes, one at a time
+            const int r = __ffs(done) - 1;
+            done &= done - 1u;
+            const unsigned tree = __shfl_sync(0xffffffffu, mine, r);
+            const int rl = __shfl_sync(0xffffffffu, len, r);
+            write_packed_row(rows + (size_t)r * pitch, rl, lane, L, g.consts, g.ovalue + (size_t)tree * L, g.otype + (size_t)tree * L,
+                             g.osize + (size_t)tree * L);
         }
+        __syncwarp();                                                       // the rows were read; their lanes may overwrite them
+        if (fin) {
+            mine = next + rank;
+            busy = mine < t1;
+            t.start(tree_seed(mine, k0, k1), busy);
+        }
+        next = next + handed < t1 ? next + handed : t1;
     }
 }
 
 // EVOGP_GENERATE_FAST=0 keeps the one-size-fits-all kernel (the A/B switch of profiles/; default on)
+static const int g_generate_balanced = []() { const char *e = getenv("EVOGP_GENERATE_BALANCED"); return e ? atoi(e) : -1; }();
+static int g_sm_count_gen() {
+    thread_local int dev_cached = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        dev_cached = dev;
+    }
+    return sms > 0 ? sms : 148;
+}
 static const bool g_generate_fast = []() { const char *e = getenv("EVOGP_GENERATE_FAST"); return !(e && e[0] == '0'); }();
 
 static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsigned varLen, unsigned outLen,
@@ -214,6 +276,20 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
         int lanes = (int)((200 * 1024) / ((size_t)a.pitch * 4) / 3);   // three CTAs per SM
         lanes = lanes >= 256 ? 256 : (lanes / 32) * 32;
         if (lanes < 32) lanes = (size_t)a.pitch * 4 * 32 <= 220 * 1024 ? 32 : 0;
+        // EVOGP_GENERATE_BALANCED=<CTAs per SM, 1..3> (default: by population size) runs the lane-re-arming kernel with a
+        // grid of that many CTAs per SM; 0 keeps one tree per lane
+        if (lanes == 256 && g_generate_balanced != 0 && popSize >= 64u * 8u * (unsigned)g_sm_count_gen()) {
+            const unsigned sms = (unsigned)g_sm_count_gen();
+            unsigned c = g_generate_balanced > 0 ? (unsigned)g_generate_balanced : (popSize + sms * 8u * 24u) / (sms * 8u * 48u);
+            c = c < 1u ? 1u : (c > 3u ? 3u : c);
+            const unsigned warps = sms * c * 8u;
+            a.trees_per_block = (int)((popSize + warps - 1u) / warps);       // trees per warp
+            const size_t smem = (size_t)256 * a.pitch * 4;
+            EVOGP_CUDA(cudaFuncSetAttribute(generate_balanced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            generate_balanced_kernel<<<sms * c, 256, smem, st>>>(a);
+            count_launch();
+            return check_launch("generate");
+        }
         if (lanes >= 32) {
             a.trees_per_block = lanes;
             const size_t smem = (size_t)lanes * a.pitch * 4;

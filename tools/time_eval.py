@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Device-side timing of the evaluation step at a BASELINE config, lowering and replay apart (developer tool).
-    python tools/time_eval.py [config 2|3] [reps]   (EVOGP_B200_LIB=<variant .so> selects another build)"""
+    python tools/time_eval.py [config 2|3] [reps]   (EVOGP_B200_LIB=<variant .so> selects another build;
+    TIME_FUNCS="if,+,pow,..." / TIME_LAYERS=n replace the config's function set / generation depth)"""
 import ctypes
 import json
 import os
@@ -22,7 +23,12 @@ def main():
     w = bench.WORKLOADS[cfg]
     dev = torch.device("cuda", 0)
     X, y = bench.dataset(w, dev)
-    d = GenerateDescriptor(**bench.descriptor_args(w))
+    da = bench.descriptor_args(w)
+    if os.environ.get("TIME_FUNCS"):
+        da["using_funcs"] = os.environ["TIME_FUNCS"].split(",")
+    if os.environ.get("TIME_LAYERS"):
+        da["max_layer_cnt"] = int(os.environ["TIME_LAYERS"])
+    d = GenerateDescriptor(**da)
     P = w["pop"] if cfg == 2 else 125000
     pops = [Forest.generate_with_keys(P, d, bench.keys_for(r, dev)) for r in range(4)]
     abi = _native.abi()
@@ -66,7 +72,8 @@ def main():
     f = torch.nan_to_num(fit, nan=0.0, posinf=0.0, neginf=0.0).clamp(max=1e6)
     print(json.dumps({"lib": os.environ.get("EVOGP_B200_LIB", "default"), "config": cfg, "pop": P, "step_us": step * 1e3, "replay_us": rep * 1e3,
                       "lower_us": (step - rep) * 1e3, "sm_mhz": clock, "tree_evals_per_s": P * w["N"] / (step * 1e-3),
-                      "fitness_digest": float(f.double().sum()), "env": {k: v for k, v in os.environ.items() if k.startswith("EVOGP_")}}))
+                      "fitness_digest": float(f.double().sum()),
+                      "mean_len": float(pops[0].batch_subtree_size[:, 0].float().mean()), "funcs": os.environ.get("TIME_FUNCS", "config"), "env": {k: v for k, v in os.environ.items() if k.startswith("EVOGP_")}}))
 
 
 if __name__ == "__main__":
