@@ -278,7 +278,10 @@ static int generate_impl(bool philox, unsigned popSize, unsigned maxGPLen, unsig
         if (lanes < 32) lanes = (size_t)a.pitch * 4 * 32 <= 220 * 1024 ? 32 : 0;
         // EVOGP_GENERATE_BALANCED=<CTAs per SM, 1..3> (default: by population size) runs the lane-re-arming kernel with a
         // grid of that many CTAs per SM; 0 keeps one tree per lane
-        if (lanes == 256 && g_generate_balanced != 0 && popSize >= 64u * 8u * (unsigned)g_sm_count_gen()) {
+        // (measured, profiles/README.md: 100000 trees - one wave of the one-tree-per-lane kernel - 64 us against 71 us re-armed;
+        //  500000 trees 280 -> 242 us, 1000000 trees 510 -> 430 us)
+        const bool many = popSize >= 5u * 768u * (unsigned)g_sm_count_gen() / 2u;      // 2.5 trees per resident lane and more
+        if (lanes == 256 && g_generate_balanced != 0 && (g_generate_balanced > 0 ? popSize >= 64u * 8u * (unsigned)g_sm_count_gen() : many)) {
             const unsigned sms = (unsigned)g_sm_count_gen();
             unsigned c = g_generate_balanced > 0 ? (unsigned)g_generate_balanced : (popSize + sms * 8u * 24u) / (sms * 8u * 48u);
             c = c < 1u ? 1u : (c > 3u ? 3u : c);

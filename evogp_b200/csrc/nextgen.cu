@@ -166,6 +166,9 @@ struct NextGenBatchArgs {
     int pitch;     // words per donor row (odd)
 };
 
+// NJ = ceil(max_tree_len / 32) when that is 1 or 2: the row loops are unrolled and phase B is software-pipelined (below);
+// NJ = 0: any row width, children strictly one after the other.
+template <int NJ>
 __global__ void __launch_bounds__(256) nextgen_batch_kernel(NextGenBatchArgs gb) {
     const NextGenArgs &g = gb.a;
     extern __shared__ __align__(16) uint32_t ng_smem[];
@@ -219,7 +222,94 @@ __global__ void __launch_bounds__(256) nextgen_batch_kernel(NextGenBatchArgs gb)
         const int my_dlen = grow_tree_packed(tree_seed((uint32_t)mine, k0 ^ 0x5bd1e995u, k1), mutate, s_leaf, s_roul, mono, g.V, g.S,
                                              gb.magicV, gb.magicS, g.constProb, L, my_donor);
         __syncwarp();
-        // ---- phase B: the warp builds the 32 children one after the other ----
+        // ---- phase B: the warp builds the 32 children one after the other.  Pipelined form (rows of <= 64 slots, no elite
+        //      in the batch): the gather of child i + 1 - its two parents' spans, 3 loads per slot - is issued before child i
+        //      is assembled and written, so its latency hides behind that work instead of stalling the warp twice per child
+        //      (ncu before: long_scoreboard 5.3 warps per issue, 16 % of the DRAM bandwidth) ----
+        bool pipelined = false;
+        if constexpr (NJ > 0) pipelined = batch * 32 >= g.elite;
+        if constexpr (NJ > 0) {
+            if (pipelined) {
+                struct Gather {
+                    uint32_t v[NJ];
+                    int t[NJ], s[NJ];
+                    SplicePlan cx;
+                };
+                auto gather = [&](int i, Gather &G) {
+                    const size_t lrow = (size_t)__shfl_sync(0xffffffffu, my_l, i) * L, rrow = (size_t)__shfl_sync(0xffffffffu, my_r, i) * L;
+                    const int llen = __shfl_sync(0xffffffffu, my_llen, i), rlen = __shfl_sync(0xffffffffu, my_rlen, i);
+                    const int lpos = __shfl_sync(0xffffffffu, my_lpos, i), rpos = __shfl_sync(0xffffffffu, my_rpos, i);
+                    const int lsub = __shfl_sync(0xffffffffu, my_lsub, i), rsub = __shfl_sync(0xffffffffu, my_rsub, i);
+                    const bool rows_ok = llen >= 1 && llen <= L && rlen >= 1 && rlen <= L;
+                    G.cx = plan_splice(llen, lpos, lsub, rpos, rsub, L, rows_ok);
+#pragma unroll
+                    for (int k = 0; k < NJ; ++k) {
+                        const int j = lane + 32 * k;
+                        G.v[k] = 0; G.t[k] = 0; G.s[k] = 0;
+                        if (j < G.cx.newlen && batch * 32 + i < g.P) {
+                            const size_t q = j < G.cx.pos ? lrow + j : (j < G.cx.pos + G.cx.dsub ? rrow + G.cx.dpos + j - G.cx.pos : lrow + j - G.cx.diff);
+                            G.v[k] = __float_as_uint(g.value[q]);
+                            G.t[k] = g.type[q];
+                            G.s[k] = g.size[q];
+                        }
+                    }
+                };
+                Gather cur;
+                gather(0, cur);
+                for (int i = 0; i < 32; ++i) {
+                    const int n = batch * 32 + i;
+                    if (n >= g.P) break;
+                    Gather nxt;
+                    if (i + 1 < 32) gather(i + 1, nxt);            // in flight while child i is assembled and written
+                    const SplicePlan cx = cur.cx;
+#pragma unroll
+                    for (int k = 0; k < NJ; ++k) {                  // the crossover child, in shared memory
+                        const int j = lane + 32 * k;
+                        if (j < L) {
+                            int sz = cur.s[k];
+                            if (j < cx.pos && j + sz > cx.pos) sz += cx.diff;            // ancestor of the splice point
+                            cv[j] = cur.v[k];
+                            cts[j] = (uint32_t)(uint16_t)cur.t[k] | ((uint32_t)(uint16_t)sz << 16);
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t mut_word = __shfl_sync(0xffffffffu, q1.y, i);
+                    const int dlen = __shfl_sync(0xffffffffu, mutate ? my_dlen : -1, i);      // -1: no mutation for this child
+                    SplicePlan mu = plan_splice(cx.newlen, cx.newlen, 0, 0, 0, L, false);      // identity
+                    if (dlen >= 0) {
+                        const int mpos = (int)(mut_word % (uint32_t)max(cx.newlen, 1));
+                        mu = plan_splice(cx.newlen, mpos, (int)(cts[mpos] >> 16), 0, dlen, L, dlen >= 1);
+                    }
+                    const uint32_t *drow = donors + (size_t)i * pitch;
+                    float *ov = g.ovalue + (size_t)n * L;
+                    int16_t *ot = g.otype + (size_t)n * L;
+                    int16_t *os = g.osize + (size_t)n * L;
+#pragma unroll
+                    for (int k = 0; k < NJ; ++k) {                  // child (or mutated child) -> global, zero-filled tail
+                        const int j = lane + 32 * k;
+                        if (j >= L) break;
+                        uint32_t v = 0, t = 0, sz = 0;
+                        if (j < mu.newlen) {
+                            if (j < mu.pos) {
+                                v = cv[j]; t = cts[j] & 0xFFFFu; sz = cts[j] >> 16;
+                                if (j + (int)sz > mu.pos) sz += mu.diff;
+                            } else if (j < mu.pos + mu.dsub) {
+                                decode_packed_node(drow[j - mu.pos], g.consts, v, t, sz);
+                            } else {
+                                const int q = j - mu.diff;
+                                v = cv[q]; t = cts[q] & 0xFFFFu; sz = cts[q] >> 16;
+                            }
+                        }
+                        ov[j] = __uint_as_float(v);
+                        ot[j] = (int16_t)t;
+                        os[j] = (int16_t)sz;
+                    }
+                    __syncwarp();
+                    cur = nxt;
+                }
+            }
+        }
+        if (!pipelined)
         for (int i = 0; i < 32; ++i) {
             const int n = batch * 32 + i;
             if (n >= g.P) break;
@@ -331,11 +421,13 @@ extern "C" int evogp_next_generation(int popSize, int gpLen, const float *value,
         while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;      // three CTAs per SM at max_tree_len 64
         const size_t smem = warps * per_warp;
         if (smem <= 200 * 1024) {
-            if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(nextgen_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static const bool pipeline = []() { const char *e = getenv("EVOGP_NEXTGEN_PIPELINE"); return !(e && e[0] == '0'); }();   // A/B switch
+            auto kern = !pipeline || gpLen > 64 ? nextgen_batch_kernel<0> : (gpLen > 32 ? nextgen_batch_kernel<2> : nextgen_batch_kernel<1>);
+            if (smem > 48 * 1024) EVOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             long long grid = (((long long)popSize + 31) / 32 + warps - 1) / warps;
             const long long cap = (long long)sms * 3;
             if (grid > cap) grid = cap;
-            nextgen_batch_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(gb);
+            kern<<<(unsigned)grid, warps * 32, smem, st>>>(gb);
             count_launch();
             return check_launch("next_generation");
         }

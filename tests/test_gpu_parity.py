@@ -35,10 +35,10 @@ GEN_CASES = [
     (1000, 33, 2, 2, ARITH_FUNCS + ["sin"], 5, (9, 8)),      # odd row width
     (64, 1024, 5, 1, ARITH_FUNCS, 9, (3, 1)),               # widest rows
     (1, 16, 1, 1, ["neg"], 3, (0, 0)),
-    # populations large enough for the lane-re-arming kernel (generate.cu generate_balanced_kernel): spans of 42 / 85 trees
-    (100000, 64, 3, 1, ARITH_FUNCS, 6, (1000, 7)),
+    (100000, 64, 3, 1, ARITH_FUNCS, 6, (1000, 7)),            # configs[1]: one full wave of the one-tree-per-lane kernel
+    # populations large enough for the lane-re-arming kernel (generate.cu generate_balanced_kernel): spans of ~85 trees
     (300001, 64, 10, 1, ALL_FUNCS, 4, (5, 6)),                # ragged last span
-    (90001, 33, 2, 1, ARITH_FUNCS + ["sin"], 5, (9, 8)),      # odd row width
+    (290001, 33, 2, 1, ARITH_FUNCS + ["sin"], 5, (9, 8)),     # odd row width
 ]
 
 
