@@ -6,3 +6,10 @@ and `lib/evogp_cuda_ops.so` (the `torch.ops.evogp_cuda.*` operator library).  Th
 CPU fallback: importing the tree package without the built libraries raises.
 """
 __version__ = "0.1.0"
+
+
+def set_replay_width(datapoints_per_lane: int):
+    """Evaluation kernel width: 0 automatic (default), 8 or 16 datapoints per lane; see include/evogp_b200.h
+    `evogp_eval_set_replay_width`.  `Forest.random_generate` sets it from the descriptor's function set."""
+    from . import _native
+    _native.set_replay_width(datapoints_per_lane)

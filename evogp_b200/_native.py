@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "evogp_version", "evogp_last_error", "evogp_launch_count", "evogp_generate", "evogp_mutate", "evogp_crossover",
     "evogp_eval_workspace_bytes", "evogp_eval_set_timing_events", "evogp_evaluate", "evogp_SR_fitness", "evogp_batch_forward",
     "evogp_SR_fitness_host", "evogp_host_release", "evogp_next_generation", "evogp_SR_fitness_scatter", "evogp_debug_lower", "evogp_classification_accuracy", "evogp_generate_philox", "evogp_extract_subtree",
-    "evogp_tournament_select", "evogp_push_fitness",
+    "evogp_tournament_select", "evogp_push_fitness", "evogp_eval_set_replay_width",
 )
 
 
@@ -70,6 +70,9 @@ def abi():
     L.evogp_classification_accuracy.argtypes = [u, u, u, u, u, vp, vp, vp, vp, vp, f, vp, vp, sz, vp]
     L.evogp_debug_lower.restype = i
     L.evogp_debug_lower.argtypes = [u, u, u, u, vp, vp, vp, i, i, vp, sz, vp, vp]
+    if hasattr(L, "evogp_eval_set_replay_width") or not os.environ.get("EVOGP_B200_LIB"):   # older A/B builds lack it
+        L.evogp_eval_set_replay_width.restype = i
+        L.evogp_eval_set_replay_width.argtypes = [i]
     L.evogp_eval_set_timing_events.restype = None
     L.evogp_eval_set_timing_events.argtypes = [vp, vp]
     for name in ("evogp_generate", "evogp_mutate", "evogp_crossover", "evogp_evaluate", "evogp_SR_fitness",
@@ -94,6 +97,24 @@ def load_ops():
     abi()
     torch.ops.load_library(OPS_PATH)
     _ops_loaded = True
+
+
+# functions whose bodies the 16-datapoints-per-lane kernel keeps next to its dispatch loop (csrc/gen_fastpath.py HOT_*)
+_HOT_FUNCS = frozenset({"+", "-", "*", "/", "neg", "sin", "cos"})
+
+
+def set_replay_width(datapoints_per_lane: int):
+    """0 = automatic, 8 or 16 datapoints per lane in the single-output evaluation kernel (include/evogp_b200.h)."""
+    check(abi().evogp_eval_set_replay_width(int(datapoints_per_lane)), "evogp_eval_set_replay_width")
+
+
+def hint_function_set(names):
+    """Called with the function names of the descriptor a forest is generated from: populations that use anything beyond
+    + - * / neg sin cos evaluate faster with 8 datapoints per lane (smaller operator bodies).
+    EVOGP_REPLAY_K in the environment overrides the hint."""
+    if names is None or os.environ.get("EVOGP_REPLAY_K") or not hasattr(abi(), "evogp_eval_set_replay_width"):
+        return
+    set_replay_width(0 if set(names) <= _HOT_FUNCS else 8)
 
 
 def launch_count():

@@ -25,6 +25,7 @@
 //        involved; K = 16 datapoints per lane in one 32-warp CTA per SM, K = 8 in
 //        four 8-warp CTAs.  Multi-output programs: their own PTX loop (K = 8), outs[] in shared
 //        memory.  Multi-GPU: evogp_push_fitness after this kernel, or the exchange flavour of it.
+#include <atomic>
 #include "replay.cuh"
 #include "lower_fast.cuh"
 
@@ -50,7 +51,10 @@ static const bool g_use_tmem_stack = []() { const char *e = getenv("EVOGP_TMEM_S
 static const bool g_k16_split = []() { const char *e = getenv("EVOGP_K16_SPLIT"); return e && e[0] == '1'; }();
 // EVOGP_FOLD=0 lowers without constant folding (the A/B switch of profiles/; default on)
 static const bool g_fold = []() { const char *e = getenv("EVOGP_FOLD"); return !(e && e[0] == '0'); }();
-static const int g_force_k = []() { const char *e = getenv("EVOGP_REPLAY_K"); return e ? atoi(e) : 0; }();
+// datapoints per lane of the single-output replay kernel: 0 = by the cost model (choose_replay), 8 or 16 forced.
+// EVOGP_REPLAY_K sets the start value, evogp_eval_set_replay_width() changes it at run time (the front-end does, from the
+// function set of the run: DESIGN.md 3.2 "function sets and the instruction cache").
+static std::atomic<int> g_force_k{[]() { const char *e = getenv("EVOGP_REPLAY_K"); return e ? atoi(e) : 0; }()};
 // optional cudaEvent_t pair recorded around the replay launch (bench.py's per-kernel timing)
 static cudaEvent_t g_ev_replay_begin = nullptr, g_ev_replay_end = nullptr;
 
@@ -205,13 +209,14 @@ static ReplayChoice choose_replay(bool multi, int mode, int N, int depth, int Lp
     // EVOGP_REPLAY_K=8|16 overrides)
     const int d = depth > 0 ? depth : 1;
     const double c8 = (double)((N + 255) / 256) * (14.0 + 16.0), c16 = (double)((N + 511) / 512) * (14.0 + 32.0);
-    const bool want16 = g_force_k ? g_force_k == 16 : c16 < c8;
+    const int force_k = g_force_k.load(std::memory_order_relaxed);
+    const bool want16 = force_k ? force_k == 16 : c16 < c8;
     // K = 16 needs room for >= 16 warps' program buffers and deep slots next to the dataset (very wide rows do not
     // leave it: they run on the 8-datapoint kernels)
     const size_t per_warp16 = (size_t)2 * Lp * 8 + (size_t)(d > kTmemSlots16 ? d - kTmemSlots16 : 0) * 512 * 4 + 16;
     const size_t staged = dataset_bytes < 48 * 1024 ? dataset_bytes : 48 * 1024;   // larger datasets are tiled to <= 48 KB
     const bool fits16 = staged + 16 * per_warp16 <= (size_t)g_max_smem && (size_t)512 * per_dp + 16 * per_warp16 <= (size_t)g_max_smem;
-    if (want16 && (fits16 || g_force_k == 16)) { c.K = 16; c.tmem = true; }
+    if (want16 && (fits16 || force_k == 16)) { c.K = 16; c.tmem = true; }
     else if (tmem_stack_cols(8, d, 8) <= 128) c.tmem = true;
     return c;
 }
@@ -310,6 +315,13 @@ extern "C" int evogp_debug_lower(unsigned popSize, unsigned gpLen, unsigned varL
 extern "C" void evogp_eval_set_timing_events(void *begin_event, void *end_event) {
     g_ev_replay_begin = static_cast<cudaEvent_t>(begin_event);
     g_ev_replay_end = static_cast<cudaEvent_t>(end_event);
+}
+
+extern "C" int evogp_eval_set_replay_width(int datapoints_per_lane) {
+    EVOGP_REQUIRE(datapoints_per_lane == 0 || datapoints_per_lane == 8 || datapoints_per_lane == 16,
+                  "replay width must be 0 (automatic), 8 or 16, got %d", datapoints_per_lane);
+    g_force_k.store(datapoints_per_lane, std::memory_order_relaxed);
+    return EVOGP_OK;
 }
 
 extern "C" size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen) {

@@ -66,10 +66,16 @@ class GenerateDescriptor:
             depth2leaf_probs = depth_schedule(max_tree_len, funcs, max_layer_cnt, layer_leaf_prob, dev)
 
         self.roulette_ufuncs = self.roulette_bfuncs = self.roulette_tfuncs = None
+        self.func_names = None     # names of the functions this descriptor can draw (None: unknown)
+        if roulette_funcs is not None:
+            cum = torch.as_tensor(roulette_funcs).detach().float().cpu()
+            steps = torch.diff(cum, prepend=torch.zeros(1))
+            self.func_names = tuple(FUNCS_NAMES[k] for k in range(min(len(FUNCS_NAMES), steps.numel())) if steps[k] > 0)
         if roulette_funcs is None:
             assert using_funcs is not None, "give either roulette_funcs or using_funcs"
             assert isinstance(using_funcs, (dict, list)), "using_funcs: a list of function names, or a dict name -> weight"
             weights = using_funcs if isinstance(using_funcs, dict) else {f: 1.0 for f in using_funcs}
+            self.func_names = tuple(f for f, wgt in weights.items() if wgt > 0)
             prob = dict2prob(weights)
             roulette_funcs = torch.cumsum(prob, dim=0, dtype=torch.float32).to(dev)
 

@@ -59,6 +59,7 @@ class Forest:
         rng="philox": counter-based Philox4x32-10 draws (`tree_generate_philox`) - same growth rules, other trees."""
         assert rng in ("taus88", "philox"), f"rng should be 'taus88' or 'philox', but got {rng}"
         d = descriptor
+        _native.hint_function_set(getattr(d, "func_names", None))      # evaluation kernel width for this function set
         op = _ops.tree_generate if rng == "taus88" else _ops.tree_generate_philox
         v, t, s = op(pop_size, d.max_tree_len, d.input_len, d.output_len, d.const_samples.shape[0],
                                      d.out_prob, d.const_prob, keys, d.depth2leaf_probs, d.roulette_funcs,

@@ -91,6 +91,17 @@ size_t evogp_eval_workspace_bytes(unsigned popSize, unsigned maxGPLen);
  * lowering pass).  Pass NULLs to switch it off. */
 void evogp_eval_set_timing_events(void *begin_event, void *end_event);
 
+/* Datapoints per lane of the single-output evaluation kernel: 16 (two passes over 1024 datapoints; the code of its
+ * + - * / neg sin cos bodies just fits the instruction cache in front of the interpreter loop), 8 (half the code per
+ * operator body: faster as soon as the population uses any other function - 15 % with + - * / sin cos tan, 2.5x with
+ * all of them) or 0 = chosen per launch from the shapes alone (the default; EVOGP_REPLAY_K presets it).
+ * The kernels cannot know the function set of a population before they have run, the caller does: the Python front-end
+ * calls this from the GenerateDescriptor a forest is generated with.  The width is a speed knob: a lane owns the same
+ * datapoints at either width and adds their errors in the same order (bit-equal fitness when dataPoints is a multiple
+ * of 512; a ragged last pass differs in the last bits).
+ * Process-wide; returns EVOGP_ERR_INVALID_ARGUMENT otherwise. */
+int evogp_eval_set_replay_width(int datapoints_per_lane);
+
 /* Diagnostics: run only the lowering pass (packed rows -> accumulator-machine programs) and copy the
  * programs out: programs = DEVICE u64[popSize][(maxGPLen + 2) & ~1].  use_fast: 1 = the register-resident pass where it
  * applies (single-output, maxGPLen <= 64), 0 = the generic pass.  deep_from: operand-stack slots >= deep_from are marked

@@ -33,6 +33,17 @@ def native():
     return _native
 
 
+@pytest.fixture(autouse=True)
+def _default_replay_width(request):
+    """The evaluation-kernel width is process-wide state the front-end sets from the function set of the last generated
+    forest (evogp_eval_set_replay_width): every GPU test starts from the automatic choice."""
+    if request.node.get_closest_marker("gpu") is not None and not os.environ.get("EVOGP_REPLAY_K"):
+        from evogp_b200 import _native
+
+        _native.set_replay_width(0)
+    yield
+
+
 # ---------------------------------------------------------------------------
 # shared builders of seeded test inputs (numpy, CPU)
 # ---------------------------------------------------------------------------

@@ -163,6 +163,60 @@ def test_sr_fitness_vs_cpu_oracle(native, orc, funcs, rtol, N):
         G.assert_close_fitness(got, want, rtol=rtol, what="vs CPU oracle")
 
 
+@pytest.mark.parametrize("funcs,layers,N", [(ALL_FUNCS, 4, 1024), (ARITH_FUNCS + ["max", "pow", "sinh", "cosh", "loose_pow", "tan"], 5, 700),
+                                            (ARITH_FUNCS, 6, 1024), (ARITH_FUNCS + ["sin", "cos", "tan"], 6, 1000)])
+def test_replay_width_is_a_speed_knob_only(native, orc, ref, funcs, layers, N):
+    """evogp_eval_set_replay_width: both kernel widths against the reference's kernels, every function on the table
+    (in the 8-datapoint loop the rare operators share one body per operator behind a second dispatch - gen_fastpath.py).
+    A lane owns the same datapoints at either width and adds their errors in the same order: with whole passes
+    (N a multiple of 512) the fitness is the same bit for bit; a ragged last pass takes the bounds-checked path, whose
+    multiply and add are not contracted, at different datapoints for the two widths (last-bit differences)."""
+    v, t, s = make_forest(orc, 3000, 64, 4, 1, funcs, layers, keys=(77, 5), consts=(-1.0, 0.5, 2.0))
+    X, y = make_data(N, 4, 1, seed=3)
+    dv, dt, ds, dX, dy = G.to_dev(v, t, s, X, y)
+    want = ref.sr_fitness(dv, dt, ds, dX, dy, True, kernel_type=4)
+    got = {}
+    try:
+        for width in (8, 16):
+            native.set_replay_width(width)
+            got[width] = G.abi_sr_fitness(native, dv, dt, ds, dX, dy, True).clone()
+            torch.cuda.synchronize()
+    finally:
+        native.set_replay_width(0)
+    for width in (8, 16):
+        G.assert_close_fitness(got[width], want, rtol=RTOL, what=f"width {width} vs reference CUDA")
+    a, b = got[8].cpu().numpy(), got[16].cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    if N % 512 == 0:
+        assert np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(b)])
+    else:
+        G.assert_close_fitness(got[8], b, rtol=1e-6, what="width 8 vs width 16")
+    with pytest.raises(RuntimeError, match="replay width"):
+        native.set_replay_width(12)
+
+
+def test_front_end_sets_the_width_from_the_descriptor(native):
+    native.load_ops()
+    from evogp_b200.tree import Forest, GenerateDescriptor
+    common = dict(max_tree_len=32, input_len=2, output_len=1, max_layer_cnt=4, const_samples=[-1.0, 0.0, 1.0])
+    d_wide = GenerateDescriptor(using_funcs=["+", "*", "max", "exp"], **common)
+    d_hot = GenerateDescriptor(using_funcs={"+": 2.0, "-": 1.0, "sin": 1.0, "tan": 0.0}, **common)
+    assert d_wide.func_names == ("+", "*", "max", "exp") and d_hot.func_names == ("+", "-", "sin")
+    d_raw = GenerateDescriptor(roulette_funcs=d_wide.roulette_funcs, depth2leaf_probs=d_wide.depth2leaf_probs, **{k: v for k, v in common.items() if k != "max_layer_cnt"})
+    assert set(d_raw.func_names) == set(d_wide.func_names)
+    X = torch.rand(300, 2, device=G.dev()); y = X[:, :1] * 2
+    f = Forest.random_generate(500, d_wide)            # width 8 from here on
+    a = f.SR_fitness(X, y)
+    native.set_replay_width(16)
+    b = f.SR_fitness(X, y)
+    torch.cuda.synchronize()
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6, equal_nan=True)
+    Forest.random_generate(10, d_hot)                  # back to the automatic choice
+    c = f.SR_fitness(X, y)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(b), torch.nan_to_num(c))     # N = 300: the automatic choice is 16 as well
+
+
 def test_fix_bug_tree_all_modes(native):
     native.load_ops()
     # reference test/fix_bug.py: fitness 0.5 whatever the execute mode
