@@ -410,14 +410,35 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
                 const uint32_t stack_base = TSTK ? tstack : smem_u32(stack + lane_off);
                 uint32_t pc_addr = prog_base, status;
                 const uint32_t xl_addr = smem_u32(xl), npb = (uint32_t)g.NP * 4u;
+#if EVOGP_FASTPATH_K16_TMEM_ASM_FUSED_LOSS
+                // K = 16: the PTX loop runs every pass of the tree and accumulates the loss itself when the passes are
+                // whole and the mode is a plain loss (gen_fastpath.py FUSED_LOSS); it comes back here only for a slow-path
+                // instruction (in whatever pass it is in) or when the last pass is done
+                uint32_t xl_cur = xl_addr, yl_cur = smem_u32(Ys + pass_off + lane_off), pass_cur = (uint32_t)pass;
+                const uint32_t loss_mode = (K == 16 && FEAT != FEAT_ACC && g.mode <= MODE_ABS && g.N % SLOT == 0)
+                                               ? (g.mode == MODE_MSE ? 1u : 2u) : 0u;
+#endif
                 for (;;) {
                     if constexpr (K == 16) {
+#if EVOGP_FASTPATH_K16_TMEM_ASM_FUSED_LOSS
+                        asm volatile(EVOGP_FASTPATH_K16_TMEM_ASM
+                                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
+                                       "+f"(acc[6]), "+f"(acc[7]), "+f"(acc[8]), "+f"(acc[9]), "+f"(acc[10]), "+f"(acc[11]),
+                                       "+f"(acc[12]), "+f"(acc[13]), "+f"(acc[14]), "+f"(acc[15]), "+r"(pc_addr), "=r"(status),
+                                       "+r"(xl_cur), "+f"(err), "+r"(yl_cur), "+r"(pass_cur)
+                                     : "r"(npb), "r"(stack_base), "r"(stack_base - 16u), "r"((uint32_t)g.npass), "r"(prog_base),
+                                       "r"(loss_mode)
+                                     : "memory");
+                        if (loss_mode != 0u && status != 0u)      // the generic step below reads this pass's columns
+                            xl = Xs + (size_t)pass_cur * SLOT + lane_off;
+#else
                         asm volatile(EVOGP_FASTPATH_K16_TMEM_ASM
                                      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
                                        "+f"(acc[6]), "+f"(acc[7]), "+f"(acc[8]), "+f"(acc[9]), "+f"(acc[10]), "+f"(acc[11]),
                                        "+f"(acc[12]), "+f"(acc[13]), "+f"(acc[14]), "+f"(acc[15]), "+r"(pc_addr), "=r"(status)
                                      : "r"(xl_addr), "r"(npb), "r"(stack_base), "r"(stack_base - 16u)
                                      : "memory");
+#endif
                     } else if constexpr (TSTK) {
                         asm volatile(EVOGP_FASTPATH_K8_TMEM_ASM
                                      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]),
@@ -436,6 +457,14 @@ __global__ void __launch_bounds__(K == 16 ? 1024 : 256, K == 16 ? 1 : ((TSTK && 
                     if (step()) break;
                     pc_addr = prog_base + ((uint32_t)pc << 3);
                 }
+#if EVOGP_FASTPATH_K16_TMEM_ASM_FUSED_LOSS
+                if constexpr (K == 16) {
+                    if (loss_mode != 0u) {     // every pass replayed and summed inside the loop
+                        pass = g.npass;
+                        continue;
+                    }
+                }
+#endif
             } else if constexpr (K == 8 && MULTI && !ROWWISE) {
                 // PTX loop for multi-output programs (fastpath_k8_multi.inc): leaf-operand forms, outs[] += in shared memory;
                 // C_IF3 and the rare operators come back here one instruction at a time
