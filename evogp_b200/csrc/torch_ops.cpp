@@ -8,12 +8,18 @@
 //     reference uses the legacy default stream and device 0 implicitly);
 //   * a failing launch raises (the reference's checks are commented out, :84,135,...);
 //   * index tensors must be int32 and node arrays f32/i16 — checked, not assumed;
-//   * one extra op, tree_batch_forward, the fused form of Forest.batch_forward.
+//   * one extra op, tree_batch_forward, the fused form of Forest.batch_forward;
+//   * tree_generate reads the function roulette it is given once (29 floats, cached by tensor identity) and sets the
+//     evaluation kernel's width for that function set (evogp_eval_set_replay_width) - the one place where a front-end
+//     that knows nothing of this library (the reference's) tells it which functions a run uses.
 // This file is plain C++ (g++): all device code lives behind the C ABI.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAGraphsC10Utils.h>
 #include <ATen/ATen.h>
 #include <torch/library.h>
+#include <cstdlib>
+#include <mutex>
 #include <tuple>
 #include "../../include/evogp_b200.h"
 
@@ -43,6 +49,34 @@ Tensor eval_workspace(int64_t pop, int64_t len, const Tensor &like, size_t &byte
     return at::empty({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte).device(like.device()));
 }
 
+// Populations of + - * / neg sin cos evaluate fastest 16 datapoints per lane, every other function set 8 per lane
+// (include/evogp_b200.h evogp_eval_set_replay_width).  The roulette is a cumulative sum: function k is in use when it
+// rises at k.  One device-to-host copy per distinct roulette tensor (identity = storage address + version counter);
+// EVOGP_REPLAY_K in the environment keeps the width fixed.
+void hint_replay_width(const Tensor &roulette) {
+    static std::mutex mu;
+    static const void *seen_ptr = nullptr;
+    static uint32_t seen_version = 0;
+    if (std::getenv("EVOGP_REPLAY_K") != nullptr) return;
+    if (c10::cuda::currentStreamCaptureStatusMayInitCtx() != c10::cuda::CaptureStatus::None) return;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (roulette.data_ptr() == seen_ptr && roulette._version() == seen_version) return;
+        seen_ptr = roulette.data_ptr();
+        seen_version = roulette._version();
+    }
+    const Tensor host = roulette.to(at::kCPU);
+    const float *cum = host.data_ptr<float>();
+    bool rare = false;
+    float below = 0.0f;
+    for (int k = 0; k < EVOGP_FUNC_END; ++k) {
+        const bool hot = (k >= 1 && k <= 4) || k == 14 || k == 15 || k == 25;      // + - * /, sin, cos, neg (kernel.h Function)
+        if (cum[k] > below && !hot) rare = true;
+        below = cum[k] > below ? cum[k] : below;
+    }
+    evogp_eval_set_replay_width(rare ? 8 : 0);
+}
+
 Tensor3 generate_impl(bool philox, int64_t pop_size, int64_t gp_len, int64_t var_len, int64_t out_len, int64_t const_samples_len,
                       double out_prob, double const_prob, Tensor keys, Tensor depth2leaf_probs, Tensor roulette_funcs,
                       Tensor const_samples) {
@@ -58,6 +92,7 @@ Tensor3 generate_impl(bool philox, int64_t pop_size, int64_t gp_len, int64_t var
     check_tensor(roulette_funcs, {EVOGP_FUNC_END}, at::kFloat, "roulette_funcs");
     check_tensor(const_samples, {const_samples_len}, at::kFloat, "const_samples");
     c10::cuda::CUDAGuard guard(keys.device());
+    hint_replay_width(roulette_funcs);
     auto out = alloc_forest(pop_size, gp_len, keys);
     auto fn = philox ? &evogp_generate_philox : &evogp_generate;
     check_rc(fn((unsigned)pop_size, (unsigned)gp_len, (unsigned)var_len, (unsigned)out_len, (unsigned)const_samples_len,
